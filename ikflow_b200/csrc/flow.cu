@@ -1,0 +1,971 @@
+// Flow half of libikflow_b200: the inverse (latent -> joint space) pass of the IKFlow conditional normalising flow.
+//
+// Replaces  output_rev, _ = self.nn_model(latent, c=conditional, rev=True)  + slice + clamp
+//           (jstmn/ikflow @ 2f4636e, ikflow/ikflow_solver.py:98-102; graph built by ikflow/model.py:291-356 out of
+//           FrEIA 0.2 GLOWCouplingBlock / PermuteRandom / FixedLinearTransform).
+//
+// One persistent kernel runs a contiguous range of coupling blocks (normally all of them) without any intermediate
+// tensor in HBM:
+//   * a ROW GROUP is 64 batch rows; rows are independent, so row groups never synchronise with each other;
+//   * a TEAM of NT = hidden/64 CTAs owns a row group; CTA t of the team owns hidden features [64t, 64t+64) of every
+//     layer.  The tiny flow state u[64][W], the condition and all coupling arithmetic are replicated in every CTA;
+//   * first layer of a subnet (K = split+cond <= 16): fp32 SIMT straight from the replicated state;
+//   * hidden x hidden layers: warp-level mma.sync.m16n8k16 bf16 tiles with fp32 accumulation, every fp32 operand
+//     split into a bf16 head and tail (head*head + head*tail + tail*head, "bf16x3").  The 64x64 weight tiles are
+//     pre-split, pre-swizzled and tile-ordered on the host so that one 16 KB bulk-TMA copy (cp.async.bulk) feeds a
+//     pipeline stage; the activation operand is the 64-row x 64-k chunk another CTA of the team produced for the
+//     previous layer, exchanged through an L2-resident scratch ring with release/acquire flags (chunk c is usable as
+//     soon as CTA c has finished -- no team-wide barrier);
+//   * last layer of a subnet (N = 2*split <= 16): every CTA reduces its own 64 features in fp32 straight from the
+//     accumulators, the NT partial sums are exchanged and summed in a fixed order by every CTA (bitwise identical
+//     replicas), then s = clamp*0.636*atan(.), y = (x - t)*exp(-s), the PermuteRandom gather, and at the very end the
+//     FixedLinearTransform inverse, the [:, :ndof] slice and the joint-limit clamp -- all in the same kernel.
+// Log-determinants are not computed (the solver discards them, ikflow_solver.py:98).
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.h"
+
+namespace ikf {
+
+constexpr int kRT = 64;               // rows per row group
+constexpr int kFT = 64;               // hidden features per CTA
+constexpr int kKC = 64;               // k elements per pipeline stage
+constexpr int kTileElems = kFT * kKC;  // 4096 bf16 = 8 KB
+constexpr int kChunkBytes = 2 * kTileElems * 2;  // head + tail = 16 KB
+constexpr int kStageBytes = 2 * kChunkBytes;     // activation chunk + weight chunk = 32 KB
+constexpr int kStages = 5;
+constexpr int kComputeWarps = 8;
+constexpr int kComputeThreads = kComputeWarps * 32;
+constexpr int kLoaderWarp = kComputeWarps;
+constexpr int kStorerWarp = kComputeWarps + 1;
+constexpr int kThreads = (kComputeWarps + 2) * 32;
+constexpr int kPad = 16;      // padded width of state / condition / small-layer dimensions
+constexpr int kMaxBig = 3;    // hidden x hidden layers per subnet (coeff_fn_config - 1)
+constexpr int kHStride = 72;  // floats per row of the fp32 reduction tile
+// per (subnet, feature tile) block of small fp32 parameters, one bulk copy:
+//   first_wT [16 k][64 f] | first_b [64] | big_b [kMaxBig][64] | last_w [16 o][64 f] | last_b [16]
+constexpr int kSmallFirstW = 0;
+constexpr int kSmallFirstB = kSmallFirstW + kPad * kFT;
+constexpr int kSmallBigB = kSmallFirstB + kFT;
+constexpr int kSmallLastW = kSmallBigB + kMaxBig * kFT;
+constexpr int kSmallLastB = kSmallLastW + kPad * kFT;
+constexpr int kSmallFloats = kSmallLastB + kPad;  // 2320
+constexpr int kSmallBytes = kSmallFloats * 4;     // 9280, multiple of 16
+static_assert(kSmallBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+constexpr float kLeakySlope = 0.01f;  // nn.LeakyReLU() default, ikflow/model.py:74-83
+
+struct FlowParams {
+  int W, s1, s2, dim_cond, nb_nodes, n_big, H, NT, ndof, precision;
+  float clamp_scale;  // rnvp_clamp * 0.636, rounded to fp32 the way torch rounds the Python scalar
+  const __nv_bfloat16* big_w;  // [subnet][n_big][NT t][NT c][head|tail][64 f][64 k] swizzled
+  const float* small;          // [subnet][NT t][kSmallFloats]
+  const int* perm_inv;         // [nb_nodes][kPad]
+  const float* m_inv;          // [kPad][kPad]  out_j = sum_i (u_i - b_i) m_inv[i][j]
+  const float* flt_b;          // [kPad]
+  const float* lo;             // [kPad] joint limits
+  const float* hi;
+  __nv_bfloat16* act;   // [slot][2][NT c][head|tail][64 r][64 k] swizzled
+  float* partial;       // [slot][2][NT t][64 r][16 o]
+  uint32_t* act_flag;   // [slot][2][NT]
+  uint32_t* part_flag;  // [slot][2][NT]
+  uint32_t* status;     // [0] status bits, [1] id of the launch that aborted
+  uint32_t epoch;       // sequence numbers of this launch start at epoch + 1
+  const float* in;
+  const float* cond;
+  float* out;
+  int in_ld, cond_ld, cond_rows, cond_cols, out_ld, out_cols;
+  int batch, block_first, block_last, finalize, clamp_out, n_rowgroups, slots;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PTX helpers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a kernel bug must surface as an error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory"); }
+// compute threads + storer warp: "the outgoing chunk is staged"
+__device__ __forceinline__ void bar_staged_arrive() {
+  asm volatile("bar.arrive 2, %0;" ::"n"(kComputeThreads + 32) : "memory");
+}
+__device__ __forceinline__ void bar_staged_sync() {
+  asm volatile("bar.sync 2, %0;" ::"n"(kComputeThreads + 32) : "memory");
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Wait until *flag has reached `expected` (wrap-safe).  Gives up (and makes every later wait of this launch give up)
+// after about a second: the results are then garbage and IKF_STATUS_SYNC_TIMEOUT is reported, but the GPU is not hung.
+__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t expected, uint32_t* status, uint32_t launch_id) {
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (true) {
+    if ((int32_t)(ld_acquire(flag) - expected) >= 0) return;
+    ++spins;
+    if (spins == 32) t0 = clock64();
+    if (spins > 32) {
+      __nanosleep(40);
+      if ((spins & 255u) == 0) {
+        if (ld_relaxed(status + 1) == launch_id) return;
+        if (clock64() - t0 > 2500000000LL) {
+          atomicOr(status, IKF_STATUS_SYNC_TIMEOUT);
+          atomicExch(status + 1, launch_id);
+          return;
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : v * kLeakySlope; }
+
+// byte offset of element (row, k) inside an 8 KB [64][64] bf16 tile: 128-byte rows, 16-byte chunks XOR-swizzled by
+// row % 8 (conflict-free ldmatrix; also the canonical K-major SWIZZLE_128B operand layout of the tensor cores)
+__device__ __host__ __forceinline__ uint32_t tile_off_bytes(int row, int k) {
+  return (uint32_t)(row * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
+}
+
+struct __align__(1024) FlowSmem {
+  uint8_t ring[kStages][kStageBytes];  // [activation head|tail][weight head|tail]
+  uint8_t staging[kChunkBytes];        // outgoing activation chunk (head|tail)
+  float htile[kRT * kHStride];         // fp32 tile for the split-k reduction
+  float small[2][kSmallFloats];
+  float u[kRT][kPad];      // flow state
+  float cnd[kRT][kPad];    // condition (first 8 columns used)
+  float a[kRT][kPad];      // output of the last layer of the current subnet
+  uint64_t full[kStages], empty[kStages];
+  uint64_t small_full[2], small_empty[2];
+  uint64_t staging_free;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the kernel
+
+__global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  FlowSmem& sm = *reinterpret_cast<FlowSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int NT = p.NT;
+  const int slot = blockIdx.x / NT;
+  const int t = blockIdx.x % NT;
+  const uint32_t launch_id = p.epoch;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], kComputeWarps);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sm.small_full[b], 1);
+      mbar_init(&sm.small_empty[b], kComputeWarps);
+    }
+    mbar_init(&sm.staging_free, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  __syncthreads();
+
+  __nv_bfloat16* act_slot = p.act + (size_t)slot * 2 * NT * 2 * kTileElems;
+  float* part_slot = p.partial + (size_t)slot * 2 * NT * kRT * kPad;
+  uint32_t* aflag = p.act_flag + (size_t)slot * 2 * NT;
+  uint32_t* pflag = p.part_flag + (size_t)slot * 2 * NT;
+
+  const int n_blocks = p.block_first - p.block_last + 1;
+  const int steps_per_rg = 2 * n_blocks;  // subnets per row group
+  const int my_rgs = (p.n_rowgroups - slot + p.slots - 1) / p.slots;
+  const int total_steps = my_rgs * steps_per_rg;
+
+  // The three roles walk the same schedule: step g = (row group, block, subnet); within a step the layers in order.
+  // `writes` counts the activation exchanges so far: exchange number w uses scratch buffer w % 2 and flag value
+  // epoch + 1 + w / 2 ... kept as two explicit per-buffer counters below.
+
+  if (warp == kLoaderWarp) {
+    // ===== loader: bulk-TMA producer for the small-parameter blocks and the weight/activation ring =====
+    if (lane == 0) {
+      uint32_t ring_pos = 0;
+      uint32_t act_w[2] = {0, 0};  // writes so far into each activation scratch buffer
+      uint32_t xchg = 0;           // activation exchanges so far
+      auto prefetch_small = [&](int g) {
+        if (g >= total_steps) return;
+        const int b = g & 1;
+        if (g >= 2) mbar_wait(&sm.small_empty[b], ((g >> 1) - 1) & 1);
+        const int in_rg = g % steps_per_rg;
+        const int blk = p.block_first - in_rg / 2;
+        const int n = 2 * blk + (in_rg & 1);
+        mbar_arrive_expect_tx(&sm.small_full[b], kSmallBytes);
+        bulk_g2s(sm.small[b], p.small + ((size_t)n * NT + t) * kSmallFloats, kSmallBytes, &sm.small_full[b]);
+      };
+      prefetch_small(0);
+      for (int g = 0; g < total_steps; ++g) {
+        const int in_rg = g % steps_per_rg;
+        const int blk = p.block_first - in_rg / 2;
+        const int n = 2 * blk + (in_rg & 1);
+        if (p.n_big == 0) prefetch_small(g + 1);
+        for (int l = 0; l < p.n_big; ++l) {
+          // input of hidden layer l = exchange number xchg (written by the previous layer of every team member)
+          const int buf = xchg & 1;
+          const uint32_t expected = p.epoch + 1 + act_w[buf];
+          const __nv_bfloat16* wbase = p.big_w + (((size_t)n * p.n_big + l) * NT + t) * NT * 2 * kTileElems;
+          const __nv_bfloat16* abase = act_slot + (size_t)buf * NT * 2 * kTileElems;
+          for (int i = 0; i < NT; ++i) {
+            const int c = (t + i) % NT;
+            const int s = ring_pos % kStages;
+            const uint32_t use = ring_pos / kStages;
+            if (use > 0) mbar_wait(&sm.empty[s], (use - 1) & 1);
+            mbar_arrive_expect_tx(&sm.full[s], kStageBytes);
+            bulk_g2s(sm.ring[s] + kChunkBytes, wbase + (size_t)c * 2 * kTileElems, kChunkBytes, &sm.full[s]);
+            wait_flag(aflag + buf * NT + c, expected, p.status, launch_id);
+            fence_proxy_async();
+            bulk_g2s(sm.ring[s], abase + (size_t)c * 2 * kTileElems, kChunkBytes, &sm.full[s]);
+            ++ring_pos;
+            if (l == 0 && i == 0) prefetch_small(g + 1);
+          }
+          ++act_w[buf];
+          ++xchg;
+        }
+      }
+    }
+  } else if (warp == kStorerWarp) {
+    // ===== storer: publishes this CTA's activation chunk to the team =====
+    uint32_t act_w[2] = {0, 0};
+    uint32_t xchg = 0;
+    for (int g = 0; g < total_steps; ++g) {
+      for (int l = 0; l < p.n_big; ++l) {
+        const int buf = xchg & 1;
+        bar_staged_sync();  // compute warps have written + proxy-fenced the staging buffer
+        if (lane == 0) {
+          __nv_bfloat16* dst = act_slot + ((size_t)buf * NT + t) * 2 * kTileElems;
+          bulk_s2g(dst, sm.staging, kChunkBytes);
+          bulk_commit();
+          bulk_wait_all();
+          fence_proxy_async();
+          st_release(aflag + buf * NT + t, p.epoch + 1 + act_w[buf]);
+          mbar_arrive(&sm.staging_free);
+        }
+        __syncwarp();
+        ++act_w[buf];
+        ++xchg;
+      }
+    }
+  } else {
+    // ===== compute warps =====
+    const int group = warp >> 2;         // split-k half
+    const int warp_m = (warp & 3) >> 1;  // 32-row half of the tile
+    const int warp_n = warp & 1;         // 32-feature half of the tile
+    const int erow = tid >> 2;           // epilogue mapping: row, and 16-byte column groups eq and eq + 4
+    const int eq = tid & 3;
+    uint32_t ring_pos = 0;
+    uint32_t part_w[2] = {0, 0};
+    uint32_t pxchg = 0;
+    uint32_t staged = 0;  // chunks handed to the storer so far
+
+    // per-lane ldmatrix offsets inside a tile (k16 step added later)
+    const int a_row_in = (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int a_kc = lane >> 4;  // which 16-byte k chunk of the k16 step
+    const int b_row_in = (lane & 7) + (lane >> 4) * 8;
+    const int b_kc = (lane >> 3) & 1;
+
+    int g = 0;
+    for (int rg = slot; rg < p.n_rowgroups; rg += p.slots) {
+      // ---- load the flow state and the condition of this row group ----
+      for (int i = tid; i < kRT * kPad; i += kComputeThreads) {
+        const int r = i / kPad, j = i % kPad;
+        const int row = rg * kRT + r;
+        float uv = 0.f, cv = 0.f;
+        if (row < p.batch) {
+          if (j < p.W) uv = p.in[(size_t)row * p.in_ld + j];
+          if (j < p.cond_cols) cv = p.cond[(size_t)(row % p.cond_rows) * p.cond_ld + j];
+        }
+        sm.u[r][j] = uv;
+        sm.cnd[r][j] = cv;
+      }
+      bar_compute();
+
+      for (int blk = p.block_first; blk >= p.block_last; --blk) {
+        for (int sidx = 0; sidx < 2; ++sidx, ++g) {
+          const int sb = g & 1;
+          const float* sp = sm.small[sb];
+          mbar_wait(&sm.small_full[sb], (g >> 1) & 1);
+          // subnet1 reads the first half and transforms the second; subnet2 the other way round
+          const int in_off = sidx == 0 ? 0 : p.s1;
+          const int in_len = sidx == 0 ? p.s1 : p.s2;
+          const int tg_off = sidx == 0 ? p.s1 : 0;
+          const int tg_len = sidx == 0 ? p.s2 : p.s1;
+
+          float v[16];  // activations of (erow, features 8eq..8eq+7 and 32+8eq..32+8eq+7) after bias + LeakyReLU
+          // ---- first layer: fp32 SIMT from the replicated state ----
+          {
+            float acc[16];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[8 * h + e] = sp[kSmallFirstB + 32 * h + 8 * eq + e];
+            const int kin = in_len + p.dim_cond;
+            for (int k = 0; k < kin; ++k) {
+              const float x = k < in_len ? sm.u[erow][in_off + k] : sm.cnd[erow][k - in_len];
+              const float* wr = sp + kSmallFirstW + k * kFT;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float4 w0 = *reinterpret_cast<const float4*>(wr + 32 * h + 8 * eq);
+                const float4 w1 = *reinterpret_cast<const float4*>(wr + 32 * h + 8 * eq + 4);
+                acc[8 * h + 0] = fmaf(x, w0.x, acc[8 * h + 0]);
+                acc[8 * h + 1] = fmaf(x, w0.y, acc[8 * h + 1]);
+                acc[8 * h + 2] = fmaf(x, w0.z, acc[8 * h + 2]);
+                acc[8 * h + 3] = fmaf(x, w0.w, acc[8 * h + 3]);
+                acc[8 * h + 4] = fmaf(x, w1.x, acc[8 * h + 4]);
+                acc[8 * h + 5] = fmaf(x, w1.y, acc[8 * h + 5]);
+                acc[8 * h + 6] = fmaf(x, w1.z, acc[8 * h + 6]);
+                acc[8 * h + 7] = fmaf(x, w1.w, acc[8 * h + 7]);
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = leaky(acc[e]);
+          }
+
+          for (int l = 0; l <= p.n_big; ++l) {
+            if (l > 0) {
+              // ---- hidden layer l-1: bf16x3 tensor-core tiles over the NT k-chunks ----
+              float acc[2][4][4];
+#pragma unroll
+              for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) acc[mi][ni][e] = 0.f;
+              for (int i = 0; i < NT; ++i) {
+                const int s = ring_pos % kStages;
+                mbar_wait(&sm.full[s], (ring_pos / kStages) & 1);
+                const uint32_t a_hi = smem_u32(sm.ring[s]);
+                const uint32_t a_lo = a_hi + kTileElems * 2;
+                const uint32_t w_hi = a_hi + kChunkBytes;
+                const uint32_t w_lo = w_hi + kTileElems * 2;
+#pragma unroll
+                for (int kk2 = 0; kk2 < 2; ++kk2) {
+                  const int kk = group * 2 + kk2;  // k16 step inside the 64-wide chunk
+                  uint32_t ah[2][4], al[2][4], bh[2][4], bl[2][4];
+#pragma unroll
+                  for (int mi = 0; mi < 2; ++mi) {
+                    const int row = warp_m * 32 + mi * 16 + a_row_in;
+                    const uint32_t off = row * 128 + ((((kk * 2 + a_kc) ^ (row & 7)) & 7) << 4);
+                    ldsm_x4(a_hi + off, ah[mi]);
+                    ldsm_x4(a_lo + off, al[mi]);
+                  }
+#pragma unroll
+                  for (int nj = 0; nj < 2; ++nj) {
+                    const int row = warp_n * 32 + nj * 16 + b_row_in;
+                    const uint32_t off = row * 128 + ((((kk * 2 + b_kc) ^ (row & 7)) & 7) << 4);
+                    ldsm_x4(w_hi + off, bh[nj]);
+                    ldsm_x4(w_lo + off, bl[nj]);
+                  }
+#pragma unroll
+                  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) {
+                      const int nj = ni >> 1, o = (ni & 1) * 2;
+                      if (p.precision == IKF_PRECISION_BF16X3) {
+                        mma_bf16(acc[mi][ni], al[mi], bh[nj][o], bh[nj][o + 1]);
+                        mma_bf16(acc[mi][ni], ah[mi], bl[nj][o], bl[nj][o + 1]);
+                      }
+                      mma_bf16(acc[mi][ni], ah[mi], bh[nj][o], bh[nj][o + 1]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty[s]);
+                ++ring_pos;
+              }
+              // ---- split-k reduction through the fp32 tile ----
+              const int gq = lane >> 2, tq = lane & 3;
+              if (group == 0) {
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                  for (int ni = 0; ni < 4; ++ni) {
+                    const int r0 = warp_m * 32 + mi * 16 + gq, c0 = warp_n * 32 + ni * 8 + 2 * tq;
+                    *reinterpret_cast<float2*>(&sm.htile[r0 * kHStride + c0]) =
+                        make_float2(acc[mi][ni][0], acc[mi][ni][1]);
+                    *reinterpret_cast<float2*>(&sm.htile[(r0 + 8) * kHStride + c0]) =
+                        make_float2(acc[mi][ni][2], acc[mi][ni][3]);
+                  }
+              }
+              bar_compute();
+              if (group == 1) {
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                  for (int ni = 0; ni < 4; ++ni) {
+                    const int r0 = warp_m * 32 + mi * 16 + gq, c0 = warp_n * 32 + ni * 8 + 2 * tq;
+                    float2* p0 = reinterpret_cast<float2*>(&sm.htile[r0 * kHStride + c0]);
+                    float2* p1 = reinterpret_cast<float2*>(&sm.htile[(r0 + 8) * kHStride + c0]);
+                    float2 x0 = *p0, x1 = *p1;
+                    x0.x += acc[mi][ni][0];
+                    x0.y += acc[mi][ni][1];
+                    x1.x += acc[mi][ni][2];
+                    x1.y += acc[mi][ni][3];
+                    *p0 = x0;
+                    *p1 = x1;
+                  }
+              }
+              bar_compute();
+              const float* bb = sp + kSmallBigB + (l - 1) * kFT;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float4 x0 = *reinterpret_cast<const float4*>(&sm.htile[erow * kHStride + 32 * h + 8 * eq]);
+                const float4 x1 = *reinterpret_cast<const float4*>(&sm.htile[erow * kHStride + 32 * h + 8 * eq + 4]);
+                const float* b8 = bb + 32 * h + 8 * eq;
+                v[8 * h + 0] = leaky(x0.x + b8[0]);
+                v[8 * h + 1] = leaky(x0.y + b8[1]);
+                v[8 * h + 2] = leaky(x0.z + b8[2]);
+                v[8 * h + 3] = leaky(x0.w + b8[3]);
+                v[8 * h + 4] = leaky(x1.x + b8[4]);
+                v[8 * h + 5] = leaky(x1.y + b8[5]);
+                v[8 * h + 6] = leaky(x1.z + b8[6]);
+                v[8 * h + 7] = leaky(x1.w + b8[7]);
+              }
+              bar_compute();  // the tile is free for the next layer's reduction
+            }
+
+            if (l < p.n_big) {
+              // ---- publish: split into bf16 head/tail, stage the swizzled chunk, hand it to the storer ----
+              if (staged > 0) mbar_wait(&sm.staging_free, (staged - 1) & 1);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float f0 = v[8 * h + 2 * e], f1 = v[8 * h + 2 * e + 1];
+                  const __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
+                  const __nv_bfloat16 l0 = __float2bfloat16_rn(f0 - __bfloat162float(h0));
+                  const __nv_bfloat16 l1 = __float2bfloat16_rn(f1 - __bfloat162float(h1));
+                  hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                  lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                const uint32_t off = tile_off_bytes(erow, 32 * h + 8 * eq);
+                *reinterpret_cast<uint4*>(sm.staging + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(sm.staging + kTileElems * 2 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
+              fence_proxy_async();
+              bar_staged_arrive();
+              ++staged;
+            }
+          }
+
+          // ---- last layer: this CTA's 64 features of every output, in fp32 from the activations ----
+          const int pb = pxchg & 1;
+          {
+            float po[16];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) {
+              const float* wr = sp + kSmallLastW + o * kFT;
+              float s = 0.f;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float4 w0 = *reinterpret_cast<const float4*>(wr + 32 * h + 8 * eq);
+                const float4 w1 = *reinterpret_cast<const float4*>(wr + 32 * h + 8 * eq + 4);
+                s = fmaf(v[8 * h + 0], w0.x, s);
+                s = fmaf(v[8 * h + 1], w0.y, s);
+                s = fmaf(v[8 * h + 2], w0.z, s);
+                s = fmaf(v[8 * h + 3], w0.w, s);
+                s = fmaf(v[8 * h + 4], w1.x, s);
+                s = fmaf(v[8 * h + 5], w1.y, s);
+                s = fmaf(v[8 * h + 6], w1.z, s);
+                s = fmaf(v[8 * h + 7], w1.w, s);
+              }
+              s += __shfl_xor_sync(0xffffffffu, s, 1);
+              s += __shfl_xor_sync(0xffffffffu, s, 2);
+              po[o] = s;
+            }
+            // lane eq of the quad stores outputs 4eq..4eq+3
+            float4 mine;
+            mine.x = eq == 0 ? po[0] : eq == 1 ? po[4] : eq == 2 ? po[8] : po[12];
+            mine.y = eq == 0 ? po[1] : eq == 1 ? po[5] : eq == 2 ? po[9] : po[13];
+            mine.z = eq == 0 ? po[2] : eq == 1 ? po[6] : eq == 2 ? po[10] : po[14];
+            mine.w = eq == 0 ? po[3] : eq == 1 ? po[7] : eq == 2 ? po[11] : po[15];
+            float* dst = part_slot + (((size_t)pb * NT + t) * kRT + erow) * kPad + 4 * eq;
+            __stcg(reinterpret_cast<float4*>(dst), mine);
+          }
+          __threadfence();
+          bar_compute();
+          const uint32_t pexp = p.epoch + 1 + part_w[pb];
+          if (tid == 0) st_release(pflag + pb * NT + t, pexp);
+          if (warp == 0) {
+            for (int c = lane; c < NT; c += 32) wait_flag(pflag + pb * NT + c, pexp, p.status, launch_id);
+          }
+          bar_compute();
+          {
+            // fixed summation order over the team: every CTA obtains bitwise identical coefficients
+            const float4 b4 = *reinterpret_cast<const float4*>(sp + kSmallLastB + 4 * eq);
+            float4 s = b4;
+            const float* src = part_slot + ((size_t)pb * NT * kRT + erow) * kPad + 4 * eq;
+            for (int c = 0; c < NT; ++c) {
+              const float4 x = __ldcg(reinterpret_cast<const float4*>(src + (size_t)c * kRT * kPad));
+              s.x += x.x;
+              s.y += x.y;
+              s.z += x.z;
+              s.w += x.w;
+            }
+            *reinterpret_cast<float4*>(&sm.a[erow][4 * eq]) = s;
+          }
+          // this subnet's small parameters are no longer needed
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.small_empty[sb]);
+          ++part_w[pb];
+          ++pxchg;
+          bar_compute();
+          // ---- affine coupling, reverse direction: y = (x - t) * exp(-clamp * 0.636 * atan(s)) ----
+          for (int i = tid; i < kRT * tg_len; i += kComputeThreads) {
+            const int r = i / tg_len, j = i % tg_len;
+            const float sc = p.clamp_scale * atanf(sm.a[r][j]);
+            const float tr = sm.a[r][tg_len + j];
+            sm.u[r][tg_off + j] = (sm.u[r][tg_off + j] - tr) * expf(-sc);
+          }
+          bar_compute();
+        }
+        // ---- PermuteRandom reverse: u = u[:, perm_inv] ----
+        {
+          float tmp[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int i = tid + c * kComputeThreads;
+            tmp[c] = i < kRT * p.W ? sm.u[i / p.W][p.perm_inv[blk * kPad + i % p.W]] : 0.f;
+          }
+          bar_compute();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int i = tid + c * kComputeThreads;
+            if (i < kRT * p.W) sm.u[i / p.W][i % p.W] = tmp[c];
+          }
+          bar_compute();
+        }
+      }
+
+      // ---- write this row group (team member 0 only; all replicas are identical) ----
+      if (t == 0) {
+        for (int i = tid; i < kRT * p.out_cols; i += kComputeThreads) {
+          const int r = i / p.out_cols, j = i % p.out_cols;
+          const int row = rg * kRT + r;
+          if (row >= p.batch) continue;
+          float o;
+          if (p.finalize) {
+            // FixedLinearTransform reverse (x - b) @ M_inv, slice, joint-limit clamp (ikflow_solver.py:98-102)
+            o = 0.f;
+            for (int k = 0; k < p.W; ++k) o = fmaf(sm.u[r][k] - p.flt_b[k], p.m_inv[k * kPad + j], o);
+            if (p.clamp_out && j < p.ndof) o = fminf(fmaxf(o, p.lo[j]), p.hi[j]);
+          } else {
+            o = sm.u[r][j];
+          }
+          if (!isfinite(o)) atomicOr(p.status, IKF_STATUS_NONFINITE);
+          p.out[(size_t)row * p.out_ld + j] = o;
+        }
+      }
+      bar_compute();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+
+static inline uint16_t bf16_bits_rn(float f) {
+  uint32_t x;
+  std::memcpy(&x, &f, 4);
+  if ((x & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((x >> 16) | 0x40);  // NaN
+  const uint32_t lsb = (x >> 16) & 1u;
+  x += 0x7fffu + lsb;
+  return (uint16_t)(x >> 16);
+}
+static inline float bf16_bits_to_float(uint16_t b) {
+  uint32_t x = (uint32_t)b << 16;
+  float f;
+  std::memcpy(&f, &x, 4);
+  return f;
+}
+
+static bool desc_ok(const IkfFlowDesc* d) {
+  if (!d) return false;
+  if (d->ndim_tot < 2 || d->ndim_tot > IKF_MAX_WIDTH) return false;
+  if (d->dim_cond < 1 || d->dim_cond > 8) return false;
+  if (d->nb_nodes < 1 || d->nb_nodes > 256) return false;
+  if (d->coeff_fn_config < 1 || d->coeff_fn_config > 4) return false;
+  if (d->hidden < 64 || d->hidden % 64 != 0 || d->hidden > 2048) return false;
+  if (d->ndof < 1 || d->ndof > d->ndim_tot) return false;
+  if (d->precision != IKF_PRECISION_BF16X3 && d->precision != IKF_PRECISION_BF16X1) return false;
+  const int s1 = d->ndim_tot / 2, s2 = d->ndim_tot - s1;
+  if (s2 + d->dim_cond > kPad || 2 * s2 > kPad) return false;
+  return true;
+}
+
+// fp32 values per subnet in state-dict order: for each Linear weight [out,in] then bias [out]
+static size_t subnet_weight_count(const IkfFlowDesc* d, int in_dim, int out_dim) {
+  const size_t H = d->hidden;
+  size_t n = H * in_dim + H;
+  n += (size_t)(d->coeff_fn_config - 1) * (H * H + H);
+  n += (size_t)out_dim * H + out_dim;
+  return n;
+}
+
+}  // namespace ikf
+
+struct IkfFlow {
+  IkfFlowDesc desc;
+  int device = 0;
+  int num_sms = 0;
+  int NT = 0, n_big = 0, slots_max = 0;
+  void* blob = nullptr;  // one device allocation holding everything below
+  size_t blob_bytes = 0, big_w_bytes = 0;
+  ikf::FlowParams base;  // pointers + model constants; per-call fields filled at launch
+  uint32_t epoch = 1;  // doubles as launch id; 0 is "no launch aborted"
+  int last_grid = 0;
+  size_t smem_bytes = 0;
+};
+
+using namespace ikf;
+
+extern "C" {
+
+size_t ikf_flow_weight_count(const IkfFlowDesc* desc) {
+  if (!desc_ok(desc)) return 0;
+  const int s1 = desc->ndim_tot / 2, s2 = desc->ndim_tot - s1;
+  return (size_t)desc->nb_nodes * (subnet_weight_count(desc, s1 + desc->dim_cond, 2 * s2) +
+                                   subnet_weight_count(desc, s2 + desc->dim_cond, 2 * s1));
+}
+
+void ikf_flow_destroy(IkfFlow* flow) {
+  if (!flow) return;
+  if (flow->blob) {
+    DeviceGuard guard(flow->device);
+    cudaFree(flow->blob);
+  }
+  delete flow;
+}
+
+int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weights, const int64_t* perm_inv,
+                    const float* m_inv, const float* flt_b, const float* joint_lo, const float* joint_hi, int device,
+                    IkfFlow** out) {
+  if (!out) return fail(IKF_EINVAL, "ikf_flow_create: out is NULL");
+  *out = nullptr;
+  if (!desc_ok(desc))
+    return fail(IKF_EINVAL,
+                "ikf_flow_create: unsupported description (need 2<=ndim_tot<=16, dim_cond<=8, coeff_fn_config 1..4, "
+                "hidden a multiple of 64 <=2048, split+cond<=16)");
+  if (!weights || !perm_inv || !m_inv || !flt_b || !joint_lo || !joint_hi)
+    return fail(IKF_EINVAL, "ikf_flow_create: NULL parameter array");
+  if (n_weights != ikf_flow_weight_count(desc))
+    return fail(IKF_EINVAL, "ikf_flow_create: got %zu weights, the description needs %zu", n_weights,
+                ikf_flow_weight_count(desc));
+  int ndev = 0;
+  IKF_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(IKF_EDEVICE, "ikf_flow_create: no CUDA device %d", device);
+  cudaDeviceProp prop;
+  IKF_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(IKF_EDEVICE, "ikf_flow_create: device %d is sm_%d%d, this library is sm_100a only",
+                                    device, prop.major, prop.minor);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(IKF_ECUDA, "ikf_flow_create: cudaSetDevice(%d) failed", device);
+
+  IkfFlow* f = new (std::nothrow) IkfFlow();
+  if (!f) return fail(IKF_ENOMEM, "ikf_flow_create: host allocation failed");
+  f->desc = *desc;
+  f->device = device;
+  f->num_sms = prop.multiProcessorCount;
+  const int W = desc->ndim_tot, s1 = W / 2, s2 = W - s1, H = desc->hidden, NT = H / kFT;
+  const int n_big = desc->coeff_fn_config - 1, nb = desc->nb_nodes, n_sub = 2 * nb;
+  f->NT = NT;
+  f->n_big = n_big;
+  f->slots_max = std::max(1, f->num_sms / NT);
+  if (NT > f->num_sms) {
+    delete f;
+    return fail(IKF_EDEVICE, "ikf_flow_create: hidden=%d needs %d co-resident CTAs, device has %d SMs", H, NT, f->num_sms);
+  }
+
+  // ---- host-side repack ----
+  const size_t big_elems = (size_t)n_sub * n_big * NT * NT * 2 * kTileElems;
+  const size_t small_floats = (size_t)n_sub * NT * kSmallFloats;
+  std::vector<uint16_t> big(big_elems);
+  std::vector<float> small(small_floats, 0.f);
+  const float* wp = weights;
+  for (int i = 0; i < nb; ++i) {
+    for (int sidx = 0; sidx < 2; ++sidx) {
+      const int n = 2 * i + sidx;
+      const int in_dim = (sidx == 0 ? s1 : s2) + desc->dim_cond;
+      const int out_dim = 2 * (sidx == 0 ? s2 : s1);
+      // first Linear [H, in_dim], bias [H]
+      const float* w0 = wp;
+      const float* b0 = wp + (size_t)H * in_dim;
+      wp = b0 + H;
+      for (int f_ = 0; f_ < H; ++f_) {
+        float* blk = small.data() + ((size_t)n * NT + f_ / kFT) * kSmallFloats;
+        for (int k = 0; k < in_dim; ++k) blk[kSmallFirstW + k * kFT + f_ % kFT] = w0[(size_t)f_ * in_dim + k];
+        blk[kSmallFirstB + f_ % kFT] = b0[f_];
+      }
+      // hidden Linears [H, H], bias [H]
+      for (int l = 0; l < n_big; ++l) {
+        const float* w = wp;
+        const float* b = wp + (size_t)H * H;
+        wp = b + H;
+        for (int tt = 0; tt < NT; ++tt) {
+          for (int c = 0; c < NT; ++c) {
+            uint16_t* hi = big.data() + ((((size_t)n * n_big + l) * NT + tt) * NT + c) * 2 * kTileElems;
+            uint16_t* lo = hi + kTileElems;
+            for (int r = 0; r < kFT; ++r) {
+              const float* src = w + (size_t)(tt * kFT + r) * H + c * kKC;
+              for (int e = 0; e < kKC; ++e) {
+                const uint32_t off = tile_off_bytes(r, e) / 2;
+                const uint16_t hb = bf16_bits_rn(src[e]);
+                hi[off] = hb;
+                lo[off] = bf16_bits_rn(src[e] - bf16_bits_to_float(hb));
+              }
+            }
+          }
+        }
+        for (int f_ = 0; f_ < H; ++f_)
+          small[((size_t)n * NT + f_ / kFT) * kSmallFloats + kSmallBigB + l * kFT + f_ % kFT] = b[f_];
+      }
+      // last Linear [out_dim, H], bias [out_dim]
+      const float* wl = wp;
+      const float* bl = wp + (size_t)out_dim * H;
+      wp = bl + out_dim;
+      for (int tt = 0; tt < NT; ++tt) {
+        float* blk = small.data() + ((size_t)n * NT + tt) * kSmallFloats;
+        for (int o = 0; o < out_dim; ++o) {
+          for (int e = 0; e < kFT; ++e) blk[kSmallLastW + o * kFT + e] = wl[(size_t)o * H + tt * kFT + e];
+          blk[kSmallLastB + o] = bl[o];
+        }
+      }
+    }
+  }
+
+  std::vector<int> perm(nb * kPad, 0);
+  for (int i = 0; i < nb; ++i)
+    for (int j = 0; j < W; ++j) {
+      const int64_t v = perm_inv[(size_t)i * W + j];
+      if (v < 0 || v >= W) {
+        delete f;
+        return fail(IKF_EINVAL, "ikf_flow_create: perm_inv[%d][%d]=%lld out of range", i, j, (long long)v);
+      }
+      perm[i * kPad + j] = (int)v;
+    }
+  std::vector<float> consts(kPad * kPad + 3 * kPad, 0.f);
+  for (int i = 0; i < W; ++i)
+    for (int j = 0; j < W; ++j) consts[i * kPad + j] = m_inv[(size_t)i * W + j];
+  for (int j = 0; j < W; ++j) consts[kPad * kPad + j] = flt_b[j];
+  for (int j = 0; j < desc->ndof; ++j) {
+    consts[kPad * kPad + kPad + j] = joint_lo[j];
+    consts[kPad * kPad + 2 * kPad + j] = joint_hi[j];
+  }
+
+  // ---- device blob ----
+  auto align_up = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
+  const int slots = f->slots_max;
+  const size_t off_big = 0;
+  const size_t off_small = align_up(off_big + big_elems * 2);
+  const size_t off_perm = align_up(off_small + small_floats * 4);
+  const size_t off_consts = align_up(off_perm + perm.size() * 4);
+  const size_t off_act = align_up(off_consts + consts.size() * 4);
+  const size_t act_bytes = (size_t)slots * 2 * NT * kChunkBytes;
+  const size_t off_partial = align_up(off_act + act_bytes);
+  const size_t partial_bytes = (size_t)slots * 2 * NT * kRT * kPad * 4;
+  const size_t off_flags = align_up(off_partial + partial_bytes);
+  const size_t flag_bytes = ((size_t)slots * 2 * NT * 2 + 2) * 4;
+  f->blob_bytes = align_up(off_flags + flag_bytes);
+  f->big_w_bytes = big_elems * 2;
+  cudaError_t e = cudaMalloc(&f->blob, f->blob_bytes);
+  if (e != cudaSuccess) {
+    delete f;
+    return fail(IKF_ENOMEM, "ikf_flow_create: cudaMalloc(%zu) failed: %s", f->blob_bytes, cudaGetErrorString(e));
+  }
+  uint8_t* base = (uint8_t*)f->blob;
+  e = cudaMemset(base + off_act, 0, f->blob_bytes - off_act);
+  if (e == cudaSuccess && big_elems) e = cudaMemcpy(base + off_big, big.data(), big_elems * 2, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(base + off_small, small.data(), small_floats * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(base + off_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(base + off_consts, consts.data(), consts.size() * 4, cudaMemcpyHostToDevice);
+  f->smem_bytes = sizeof(FlowSmem) + 1024;
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(flow_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_bytes);
+  if (e != cudaSuccess) {
+    ikf_flow_destroy(f);
+    return fail(IKF_ECUDA, "ikf_flow_create: device setup failed: %s", cudaGetErrorString(e));
+  }
+
+  FlowParams& p = f->base;
+  std::memset(&p, 0, sizeof(p));
+  p.W = W; p.s1 = s1; p.s2 = s2; p.dim_cond = desc->dim_cond; p.nb_nodes = nb; p.n_big = n_big; p.H = H; p.NT = NT;
+  p.ndof = desc->ndof; p.precision = desc->precision;
+  p.clamp_scale = (float)((double)desc->rnvp_clamp * 0.636);
+  p.big_w = (const __nv_bfloat16*)(base + off_big);
+  p.small = (const float*)(base + off_small);
+  p.perm_inv = (const int*)(base + off_perm);
+  p.m_inv = (const float*)(base + off_consts);
+  p.flt_b = p.m_inv + kPad * kPad;
+  p.lo = p.flt_b + kPad;
+  p.hi = p.lo + kPad;
+  p.act = (__nv_bfloat16*)(base + off_act);
+  p.partial = (float*)(base + off_partial);
+  p.act_flag = (uint32_t*)(base + off_flags);
+  p.part_flag = p.act_flag + (size_t)slots * 2 * NT;
+  p.status = p.part_flag + (size_t)slots * 2 * NT;
+  *out = f;
+  return IKF_OK;
+}
+
+int ikf_flow_reserve(IkfFlow* flow, int max_batch) {
+  if (!flow || max_batch < 0) return fail(IKF_EINVAL, "ikf_flow_reserve: bad arguments");
+  return IKF_OK;  // the workspace is per team, not per row: nothing grows with the batch
+}
+
+static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* cond, int cond_ld, int cond_rows,
+                       int cond_cols, float* out, int out_ld, int out_cols, int batch, int block_first, int block_last,
+                       int finalize, int clamp, void* stream, const char* name) {
+  if (!flow) return fail(IKF_EINVAL, "%s: flow is NULL", name);
+  if (batch < 0) return fail(IKF_EINVAL, "%s: negative batch %d", name, batch);
+  if (batch == 0) return IKF_OK;
+  const IkfFlowDesc& d = flow->desc;
+  if (!in || !cond || !out) return fail(IKF_EINVAL, "%s: NULL tensor", name);
+  if (in_ld < d.ndim_tot || out_cols < 1 || out_cols > d.ndim_tot || out_ld < out_cols)
+    return fail(IKF_EINVAL, "%s: bad leading dimension / column count", name);
+  if (cond_rows < 1 || cond_cols < 1 || cond_cols > d.dim_cond || cond_ld < cond_cols)
+    return fail(IKF_EINVAL, "%s: bad condition shape (%d rows, %d cols, ld %d; dim_cond %d)", name, cond_rows,
+                cond_cols, cond_ld, d.dim_cond);
+  if (block_first >= d.nb_nodes || block_last < 0 || block_first < block_last)
+    return fail(IKF_EINVAL, "%s: bad block range [%d..%d] for %d blocks", name, block_first, block_last, d.nb_nodes);
+  DeviceGuard guard(flow->device);
+  if (!guard.ok) return fail(IKF_ECUDA, "%s: cudaSetDevice(%d) failed", name, flow->device);
+
+  FlowParams p = flow->base;
+  p.in = in; p.in_ld = in_ld; p.cond = cond; p.cond_ld = cond_ld; p.cond_rows = cond_rows; p.cond_cols = cond_cols;
+  p.out = out; p.out_ld = out_ld; p.out_cols = out_cols; p.batch = batch;
+  p.block_first = block_first; p.block_last = block_last; p.finalize = finalize; p.clamp_out = clamp;
+  p.n_rowgroups = (batch + kRT - 1) / kRT;
+  p.slots = std::min(p.n_rowgroups, flow->slots_max);
+  p.epoch = flow->epoch;
+  // every flag of this launch stays below epoch + 1 + (row groups per slot) * (subnets) * (exchanges per subnet)
+  const uint32_t rg_per_slot = (uint32_t)((p.n_rowgroups + p.slots - 1) / p.slots);
+  flow->epoch += rg_per_slot * 2u * (uint32_t)(block_first - block_last + 1) * (uint32_t)(flow->n_big + 1) + 2u;
+
+  const int grid = p.slots * flow->NT;
+  flow->last_grid = grid;
+  void* args[] = {(void*)&p};
+  // cooperative launch = the driver guarantees that all CTAs of all teams are co-resident (the teams spin on each
+  // other's flags)
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)flow_inverse_kernel, dim3(grid), dim3(kThreads), args,
+                                              flow->smem_bytes, (cudaStream_t)stream);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return fail(IKF_ECUDA, "%s: launch failed: %s", name, cudaGetErrorString(e));
+  return IKF_OK;
+}
+
+int ikf_flow_inverse(IkfFlow* flow, const float* latent, int latent_ld, const float* cond, int cond_ld, int cond_rows,
+                     int cond_cols, float* out, int out_ld, int out_cols, int batch, int clamp, void* stream) {
+  if (!flow) return fail(IKF_EINVAL, "ikf_flow_inverse: flow is NULL");
+  return flow_launch(flow, latent, latent_ld, cond, cond_ld, cond_rows, cond_cols, out, out_ld, out_cols, batch,
+                     flow->desc.nb_nodes - 1, 0, 1, clamp, stream, "ikf_flow_inverse");
+}
+
+int ikf_flow_inverse_blocks(IkfFlow* flow, const float* state_in, int in_ld, const float* cond, int cond_ld,
+                            int cond_rows, int cond_cols, float* state_out, int out_ld, int batch, int block_first,
+                            int block_last, void* stream) {
+  if (!flow) return fail(IKF_EINVAL, "ikf_flow_inverse_blocks: flow is NULL");
+  return flow_launch(flow, state_in, in_ld, cond, cond_ld, cond_rows, cond_cols, state_out, out_ld,
+                     flow->desc.ndim_tot, batch, block_first, block_last, 0, 0, stream, "ikf_flow_inverse_blocks");
+}
+
+int ikf_flow_status(IkfFlow* flow, void* stream, uint32_t* status_out) {
+  if (!flow || !status_out) return fail(IKF_EINVAL, "ikf_flow_status: bad arguments");
+  DeviceGuard guard(flow->device);
+  if (!guard.ok) return fail(IKF_ECUDA, "ikf_flow_status: cudaSetDevice(%d) failed", flow->device);
+  uint32_t host[2] = {0, 0};
+  IKF_CUDA(cudaMemcpyAsync(host, flow->base.status, sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  IKF_CUDA(cudaMemsetAsync(flow->base.status, 0, sizeof(uint32_t), (cudaStream_t)stream));
+  IKF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  *status_out = host[0];
+  return IKF_OK;
+}
+
+int ikf_flow_info(IkfFlow* flow, size_t* packed_weight_bytes, int* grid_ctas_last, int* smem_bytes) {
+  if (!flow) return fail(IKF_EINVAL, "ikf_flow_info: flow is NULL");
+  if (packed_weight_bytes) *packed_weight_bytes = flow->big_w_bytes + (size_t)2 * flow->desc.nb_nodes * flow->NT * kSmallBytes;
+  if (grid_ctas_last) *grid_ctas_last = flow->last_grid;
+  if (smem_bytes) *smem_bytes = (int)flow->smem_bytes;
+  return IKF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,258 @@
+"""``IKFlowSolver`` -- same public surface as ``ikflow/ikflow_solver.py`` of the reference (jstmn/ikflow @ 2f4636e),
+with the two operator calls of the hot path served by the sm_100a engine:
+
+* ``generate_ik_solutions``        -> one launch of the fused inverse-flow kernel (``csrc/flow.cu``); the condition
+  tensor, the ``[:, :ndof]`` slice and the joint-limit clamp are folded into that launch.
+* ``generate_exact_ik_solutions``  -> the same launch for ``n * repeat_count`` seeds followed by ONE launch of the
+  device-side Levenberg-Marquardt / select loop (``csrc/robot.cu``) per pass, instead of the reference's
+  O(100)-launch LM step, per-row Python selection loop and three host syncs per LM iteration
+  (``ikflow_solver.py:201-233``).
+
+Argument checks raise ``AssertionError`` exactly where the reference asserts (``:311-326,359-362``).
+"""
+
+import pickle
+from time import time
+from typing import Callable, Dict, Optional, Tuple, Union
+
+import torch
+
+from .config import DEFAULT_TORCH_DTYPE, DEVICE
+from .evaluation_utils import SOLUTION_EVALUATION_RESULT_TYPE, evaluate_solutions
+from .model import IkflowModelParameters, glow_cNF_model
+from .robots import Robot
+
+
+def mm_to_m(x: float) -> float:
+    return x / 1000.0
+
+
+def draw_latent(latent_distribution: str, latent_scale: float, shape: Tuple[int, int], device: str):
+    """Draw a sample from the latent noise distribution for running inference (``ikflow_solver.py:16-29``)."""
+    assert latent_distribution in ["gaussian", "uniform"]
+    assert latent_scale > 0
+    assert len(shape) == 2
+    if latent_distribution == "gaussian":
+        return latent_scale * torch.randn(shape, device=device)
+    if latent_distribution == "uniform":
+        return 2 * latent_scale * torch.rand(shape, device=device) - latent_scale
+
+
+class IKFlowSolver:
+    def __init__(self, hyper_parameters: IkflowModelParameters, robot: Robot, compile_model: Optional[Dict] = None):
+        """Initialize an IKFlowSolver (``ikflow_solver.py:33-68``).  ``compile_model`` is accepted for interface
+        compatibility and ignored: there is no graph to compile, the whole reverse pass already is one kernel."""
+        assert isinstance(
+            hyper_parameters, IkflowModelParameters
+        ), f"hyper_parameters should be a IkflowModelParameters type, is {type(hyper_parameters)}"
+        assert isinstance(robot, Robot), f"robot should be a Robot type, is {type(robot)}"
+        assert isinstance(compile_model, (type(None), dict))
+
+        if not hasattr(hyper_parameters, "sigmoid_on_output"):
+            hyper_parameters.sigmoid_on_output = False
+        if hyper_parameters.softflow_enabled:
+            assert (
+                not hyper_parameters.sigmoid_on_output
+            ), "sigmoid_on_output and softflow are incompatible, disable one or the other"
+        self._robot = robot
+        self.dim_cond = 7
+        if hyper_parameters.softflow_enabled:
+            self.dim_cond = 8  # [x, ... q3, softflow_scale]   (softflow_scale should be 0 for inference)
+        self._network_width = hyper_parameters.dim_latent_space
+        self._do_compile_model = compile_model is not None
+        self._model_weights_loaded = False
+        self.nn_model = glow_cNF_model(hyper_parameters, self._robot, self.dim_cond, self._network_width)
+        self.ndof = self.robot.ndof
+
+    @property
+    def robot(self) -> Robot:
+        return self._robot
+
+    @property
+    def network_width(self) -> int:
+        return self._network_width
+
+    @property
+    def conditional_size(self) -> int:
+        """Dimensionality of the conditional vector: 7 = [x, y, z, q0, q1, q2, q3], 8 with softflow (the softflow value
+        is 0 for inference)."""
+        return self.dim_cond
+
+    def _run_inference(
+        self,
+        latent: torch.Tensor,
+        conditional: torch.Tensor,
+        t0: float,
+        clamp_to_joint_limits: bool,
+        return_detailed: bool,
+    ):
+        """Run the network (``ikflow_solver.py:85-110``).  ``conditional`` is [n x 7|8]; it may also have fewer rows
+        than ``latent`` (1 = one pose for all, n = repeat-major tiling): the kernel indexes row ``i % rows`` instead of
+        materialising the tiled tensor."""
+        assert latent.shape[0] % conditional.shape[0] == 0, f"{len(latent)} != {len(conditional)}"
+        t0 = time()
+        # nn_model(latent, c=conditional, rev=True)[0][:, :ndof] + robot.clamp_to_joint_limits, in one launch
+        solutions = self.nn_model.inverse(latent, conditional, out_cols=self.ndof, clamp=clamp_to_joint_limits)
+        if return_detailed:
+            pos_errors, rot_errors, joint_limits_exceeded, self_collisions = evaluate_solutions(
+                self.robot, conditional[:, 0:7], solutions
+            )
+            return solutions, pos_errors, rot_errors, joint_limits_exceeded, self_collisions, time() - t0
+        return solutions
+
+    def _calculate_pose_error(self, qs: torch.Tensor, target_poses: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``ikflow_solver.py:112-117``: FK, L2 position error and quaternion geodesic, fused."""
+        return self.robot.pose_errors(qs, target_poses)
+
+    def _generate_exact_ik_solutions(
+        self,
+        target_poses: torch.Tensor,
+        repeat_count: int,
+        n_opt_steps_max: int,
+        pos_error_threshold: float,
+        rot_error_threshold: float,
+        printc: Callable[[str], None],
+        run_lma_on_cpu: bool = False,
+    ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """One pass of ``ikflow_solver.py:119-247``: ``repeat_count`` flow seeds per pose (rows repeat-major), then up to
+        ``n_opt_steps_max`` LM steps; a pose is solved at the first step where one of its seeds meets both thresholds and
+        takes the solution of the LAST such seed.  ``run_lma_on_cpu`` is accepted and ignored (everything stays on
+        the GPU; the CPU detour of the reference exists only to dodge launch overhead)."""
+        t0 = time()
+        n = target_poses.shape[0]
+        n_tiled = n * repeat_count
+        device = target_poses.device
+        with torch.inference_mode():
+            latent = draw_latent("gaussian", 1.0, (n_tiled, self._network_width), device)
+            q = self._run_inference(latent, target_poses, t0, True, False)
+            t_ikf = time() - t0
+            final_solutions, final_valids, _ = self.robot.lm_refine(
+                target_poses, q, repeat_count, n_opt_steps_max, pos_error_threshold, rot_error_threshold
+            )
+            printc("  t_ikf (launch):", t_ikf)
+            return final_solutions, final_valids
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # --- Public methods
+    #
+
+    def generate_ik_solutions(
+        self,
+        y: torch.Tensor,
+        n: Optional[int] = None,
+        latent: Optional[torch.Tensor] = None,
+        latent_distribution: str = "gaussian",
+        latent_scale: float = 1.0,
+        clamp_to_joint_limits: bool = True,
+        refine_solutions: bool = False,
+        return_detailed: bool = False,
+        allow_uninitialized: bool = False,
+    ) -> Union[torch.Tensor, SOLUTION_EVALUATION_RESULT_TYPE]:
+        """Run the network in reverse to generate samples conditioned on a pose y (``ikflow_solver.py:254-343``).
+
+        ``y`` is a single pose [7] = [x, y, z, qw, qx, qy, qz] (then ``n`` solutions are drawn) or a batch [n x 7]
+        (one solution per pose).  Returns [n x ndof], or with ``return_detailed`` the 6-tuple
+        (solutions, pos_errors, rot_errors, joint_limits_exceeded, self_colliding, runtime).
+        """
+        t0 = time()
+        if not allow_uninitialized:
+            assert self._model_weights_loaded, "Model weights have not been loaded. Call load_state_dict(...)"
+        assert isinstance(y, torch.Tensor), f"y must be a torch.Tensor (got {type(y)})."
+        if y.numel() == 7:
+            assert isinstance(n, int)
+            assert n > 0
+        else:
+            assert y.shape[1] == 7, f"y must be of shape [7] or [n x 7], got {y.shape}"
+        assert isinstance(latent_distribution, str)
+        assert isinstance(latent_scale, float)
+        assert isinstance(latent, torch.Tensor) or (
+            latent is None
+        ), f"latent must either be a torch.Tensor or None (got {type(latent)})."
+        assert not refine_solutions, "refine_solutions is deprecated, use generate_exact_ik_solutions() instead"
+        if "cuda" in str(DEVICE):
+            assert "cpu" not in str(y.device), f"Cuda is available ('{DEVICE}'), but target_poses are on {y.device}"
+
+        n = y.shape[0] if n is None else n
+        device = y.device
+        with torch.inference_mode():
+            # The reference concatenates [y, 0] into an [n x 8] conditional (:333-338); the kernel reads the 7 pose
+            # columns (one row broadcast for a single pose) and supplies the zero softflow column itself.
+            conditional = y.reshape(1, 7) if y.numel() == 7 else y
+            if latent is None:
+                latent = draw_latent(latent_distribution, latent_scale, (n, self._network_width), device)
+            assert latent.shape[0] == n, f"{latent.shape[0]} != {n}"
+            return self._run_inference(latent, conditional, t0, clamp_to_joint_limits, return_detailed)
+
+    # The batched [n x 7] form under the name BASELINE.json's metric uses.
+    def solve_n_poses(self, target_poses: torch.Tensor, **kwargs) -> torch.Tensor:
+        assert target_poses.dim() == 2 and target_poses.shape[1] == 7
+        return self.generate_ik_solutions(target_poses, None, **kwargs)
+
+    def generate_exact_ik_solutions(
+        self,
+        target_poses: torch.Tensor,
+        repeat_counts: Tuple[int] = (1, 3, 10),
+        pos_error_threshold: float = mm_to_m(1),
+        rot_error_threshold: float = 0.1,
+        verbosity: int = 0,
+        run_lma_on_cpu: bool = True,
+        return_detailed: bool = False,
+    ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Same as generate_ik_solutions() but refines solutions using Levenberg-Marquardt after they're generated
+        (``ikflow_solver.py:345-411``).  Returns (solutions [n x ndof], valids [n] bool).
+
+        NOTE: returned solutions may be self colliding
+        """
+        assert target_poses.shape[1] == 7, f"target_poses must be of shape [n x 7], got {target_poses.shape}"
+        assert isinstance(repeat_counts, tuple), f"repeat_counts must be a tuple, got {type(repeat_counts)}"
+        assert not return_detailed, "return_detailed is not currently supported for generate_exact_ik_solutions()"
+        assert self._model_weights_loaded, "Model weights have not been loaded. Call load_state_dict(...)"
+        t0 = time()
+        n_opt_steps_max = 3
+        n_retries = len(repeat_counts)
+
+        def printc(s, *args, **kwargs):
+            if verbosity > 0:
+                print(s, *args, **kwargs)
+
+        with torch.inference_mode():
+            solutions, valids = self._generate_exact_ik_solutions(
+                target_poses, repeat_counts[0], n_opt_steps_max, pos_error_threshold, rot_error_threshold, printc,
+                run_lma_on_cpu,
+            )
+            if valids.all():  # host sync, one per pass
+                printc("All solutions converged, returning")
+                return solutions, valids
+
+            for i in range(1, n_retries):
+                invalid = torch.logical_not(valids)
+                missing_target_poses = target_poses[invalid, :]
+                new_solutions, new_solution_valids = self._generate_exact_ik_solutions(
+                    missing_target_poses, repeat_counts[i], n_opt_steps_max, pos_error_threshold, rot_error_threshold,
+                    printc, run_lma_on_cpu,
+                )
+                solutions[invalid, :] = new_solutions
+                valids[invalid] = new_solution_valids
+                if new_solutions.all():  # (sic) the reference tests the solution tensor here, ikflow_solver.py:402
+                    printc(f"All missing target poses solutions converged, returning ({time() - t0} sec)")
+                    return solutions, valids
+
+            printc(f"Missing target poses not found, returning ({time() - t0} sec)")
+            return solutions, valids
+
+    def load_state_dict(self, state_dict_filename: str):
+        """Set the nn_models state_dict from a pickled FrEIA state dict (``ikflow_solver.py:413-441``)."""
+        with open(state_dict_filename, "rb") as f:
+            try:
+                state_dict = pickle.load(f)
+                self.nn_model.load_state_dict(state_dict)
+                self._model_weights_loaded = True
+            except pickle.UnpicklingError as e:
+                print(f"Error loading state dict from {state_dict_filename}: {e}")
+                raise e
+
+    def load_state_dict_from_dict(self, state_dict: Dict[str, torch.Tensor]):
+        """Convenience for in-memory (e.g. synthetic) weights; the reference reaches the same state through
+        ``solver.nn_model.load_state_dict(sd); solver._model_weights_loaded = True``."""
+        self.nn_model.load_state_dict(state_dict)
+        self._model_weights_loaded = True

@@ -1,0 +1,174 @@
+/* ikflow_b200.h -- C ABI of libikflow_b200.so, the B200 (sm_100a) engine behind the IKFlow hot path.
+ *
+ * The reference (jstmn/ikflow @ 2f4636e) is pure Python; its "FFI" for this path is the two operator
+ * boundaries its solver calls into third-party Python packages:
+ *
+ *   (1) flow        ikflow/ikflow_solver.py:98    output_rev, _ = self.nn_model(latent, c=conditional, rev=True)
+ *                   + :99-102 (slice [:, :ndof], robot.clamp_to_joint_limits)
+ *   (2) kinematics  ikflow/ikflow_solver.py:114   robot.forward_kinematics(qs)
+ *                   ikflow/ikflow_solver.py:116   geodesic_distance_between_quaternions(...)
+ *                   ikflow/ikflow_solver.py:205,208  robot.inverse_kinematics_step_levenburg_marquardt(poses, q)
+ *                   ikflow/ikflow_solver.py:201-233  the LM / select / compact loop of _generate_exact_ik_solutions
+ *
+ * Every entry point below replaces one of those calls; the reference-side binding (a ctypes stub) is shown in
+ * INTEGRATION.md.  Conventions:
+ *   - plain pointers and sizes only; all tensor pointers are DEVICE pointers owned by the caller (torch), row-major
+ *     fp32 unless stated, borrowed for the duration of the call;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream) and does
+ *     no hidden host synchronisation (exceptions are documented);
+ *   - return 0 on success, a negative IKF_E* code otherwise; never throws.  ikf_last_error() returns a thread-local
+ *     human-readable message for the last failing call;
+ *   - a handle may be used by one stream at a time (it owns the activation workspace).
+ */
+#ifndef IKFLOW_B200_H_
+#define IKFLOW_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IKF_OK 0
+#define IKF_EINVAL (-1)   /* bad argument */
+#define IKF_ECUDA (-2)    /* CUDA runtime error (see ikf_last_error) */
+#define IKF_ENOMEM (-3)   /* device allocation failed */
+#define IKF_EDEVICE (-4)  /* device is not an sm_100 part / kernel image not loadable */
+
+/* status bits reported by ikf_flow_status */
+#define IKF_STATUS_NONFINITE 1u    /* a hidden activation or an output was not finite */
+#define IKF_STATUS_SYNC_TIMEOUT 2u /* an inter-CTA dependency wait timed out (results invalid) */
+
+#define IKF_MAX_WIDTH 16  /* dim_latent_space */
+#define IKF_MAX_LINKS 16  /* links on the kinematic chain (fixed + actuated) */
+#define IKF_MAX_DOF 8     /* actuated joints handled by the kinematics kernels (one lane each) */
+
+typedef struct IkfFlow IkfFlow;
+typedef struct IkfRobot IkfRobot;
+
+/* Hyper-parameters of the conditional flow -- the fields of ikflow/model_descriptions.yaml:10-17 plus what
+ * IKFlowSolver.__init__ derives from them (ikflow/ikflow_solver.py:51-54). */
+typedef struct {
+  int32_t ndim_tot;        /* dim_latent_space (network width W), 2..IKF_MAX_WIDTH */
+  int32_t dim_cond;        /* 8 with softflow (default), 7 without -- ikflow_solver.py:51-53 */
+  int32_t nb_nodes;        /* number of [PermuteRandom, GLOWCouplingBlock] pairs -- model.py:338 */
+  int32_t coeff_fn_config; /* n_layers of subnet_constructor (1..4): n_layers+1 nn.Linear -- model.py:51-96 */
+  int32_t hidden;          /* coeff_fn_internal_size; multiple of 64 */
+  int32_t ndof;            /* robot.ndof <= ndim_tot */
+  float rnvp_clamp;        /* GLOWCouplingBlock clamp -- model.py:347 */
+  int32_t precision;       /* IKF_PRECISION_*: operand format of the hidden-layer tensor-core products */
+} IkfFlowDesc;
+
+/* Hidden 1024x1024 layers run on the tensor cores with fp32 accumulation.  BF16X3 splits every fp32 operand into a
+ * bf16 head and a bf16 tail and issues head*head + head*tail + tail*head (16 mantissa bits, fp32 exponent range:
+ * no overflow/underflow hazards) -- 3e-5 abs from the fp32 reference after 96 chained layers (scripts/precision_study.py).
+ * BF16X1 is the single-product fast mode (about 1e-2 abs): NOT parity grade, reported separately. */
+#define IKF_PRECISION_BF16X3 0
+#define IKF_PRECISION_BF16X1 1
+
+/* ---- flow --------------------------------------------------------------------------------------------------------
+ * ikf_flow_create: replaces glow_cNF_model(...) + nn_model.load_state_dict(...) (ikflow/model.py:291-356,
+ * ikflow/ikflow_solver.py:413-429).  All inputs are HOST pointers, copied/repacked during the call (synchronous).
+ *   weights   the nn.Linear parameters in state-dict order, fp32, concatenated:
+ *             for i in 0..nb_nodes-1: for subnet in (subnet1, subnet2): for each Linear: weight [out,in] then bias [out]
+ *             (keys module_list.{2+2i}.subnet{1,2}.{0,2,..}.{weight,bias})
+ *   perm_inv  [nb_nodes][ndim_tot] int64, module_list.{1+2i}.perm_inv
+ *   m_inv     [ndim_tot][ndim_tot] module_list.0.M_inv;  flt_b [ndim_tot] module_list.0.b
+ *   joint_lo/joint_hi  [ndof] robot.actuated_joints_limits (for the clamp of ikflow_solver.py:102)
+ */
+int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weights, const int64_t* perm_inv,
+                    const float* m_inv, const float* flt_b, const float* joint_lo, const float* joint_hi, int device,
+                    IkfFlow** out);
+void ikf_flow_destroy(IkfFlow* flow);
+
+/* Number of fp32 values ikf_flow_create expects in `weights` for `desc` (0 on invalid desc). */
+size_t ikf_flow_weight_count(const IkfFlowDesc* desc);
+
+/* Pre-size the activation workspace for batches up to max_batch rows (otherwise grown on demand, which synchronises). */
+int ikf_flow_reserve(IkfFlow* flow, int max_batch);
+
+/* ikf_flow_inverse: replaces ikflow_solver.py:98-102 -- the whole reverse pass glow_{nb-1}^-1, perm_{nb-1}^-1, ...,
+ * glow_0^-1, perm_0^-1, FixedLinearTransform^-1, followed (optionally) by the joint-limit clamp.
+ *   latent   [batch][ndim_tot]            (row stride latent_ld floats)
+ *   cond     [cond_rows][cond_cols]       (row stride cond_ld floats); row b of the batch uses cond row (b % cond_rows):
+ *            cond_rows == batch  -> one pose per row (ikflow_solver.py:338)
+ *            cond_rows == 1      -> one pose broadcast (y.expand, ikflow_solver.py:334-336)
+ *            cond_rows == n      -> conditional.repeat((repeat_count, 1)) of ikflow_solver.py:185
+ *            cond_cols may be dim_cond or 7; missing trailing columns are 0 (the softflow column, ikflow_solver.py:335)
+ *   out      [batch][out_cols]            (row stride out_ld floats); out_cols <= ndim_tot.  out_cols = ndim_tot gives
+ *            nn_model's raw output, out_cols = ndof the solver's `solutions`
+ *   clamp    != 0: clamp columns < ndof to the joint limits (ikflow_solver.py:101-102)
+ */
+int ikf_flow_inverse(IkfFlow* flow, const float* latent, int latent_ld, const float* cond, int cond_ld, int cond_rows,
+                     int cond_cols, float* out, int out_ld, int out_cols, int batch, int clamp, void* stream);
+
+/* The same pass restricted to coupling blocks block_first, block_first-1, ..., block_last (the order of the reverse
+ * pass; nb_nodes-1 >= block_first >= block_last >= 0): state_out = perm_{last}^-1 glow_{last}^-1 ... glow_{first}^-1
+ * (state_in).  One launch of the per-block kernel chain; used to compare against the reference block by block.
+ * state_in/state_out are [batch][ndim_tot] (row strides in floats); FixedLinearTransform^-1 and the clamp are applied
+ * only by ikf_flow_inverse. */
+int ikf_flow_inverse_blocks(IkfFlow* flow, const float* state_in, int in_ld, const float* cond, int cond_ld,
+                            int cond_rows, int cond_cols, float* state_out, int out_ld, int batch, int block_first,
+                            int block_last, void* stream);
+
+/* Reads (and clears) the device status word.  SYNCHRONISES `stream`. */
+int ikf_flow_status(IkfFlow* flow, void* stream, uint32_t* status_out);
+
+/* Introspection for benchmarks: bytes of packed weights resident in HBM, CTAs per launch, dynamic smem per CTA. */
+int ikf_flow_info(IkfFlow* flow, size_t* packed_weight_bytes, int* grid_ctas_last, int* smem_bytes);
+
+/* ---- kinematics --------------------------------------------------------------------------------------------------
+ * ikf_robot_create: replaces jrl.robots.get_robot(name) for the functions on the hot path.  HOST pointers.
+ *   kind      [n_links] 0 = fixed, 1 = revolute, 2 = prismatic (chain order base -> end effector)
+ *   fixed_T   [n_links][12] row-major 3x4 [R | p] of the joint's origin (URDF xyz/rpy), fp64
+ *   axis      [n_links][3] joint axis in the joint frame (ignored for fixed)
+ *   lo, hi    [ndof] limits of the actuated joints in chain order
+ */
+int ikf_robot_create(int n_links, const int32_t* kind, const double* fixed_T, const double* axis, const double* lo,
+                     const double* hi, int device, IkfRobot** out);
+void ikf_robot_destroy(IkfRobot* robot);
+int ikf_robot_ndof(const IkfRobot* robot);
+
+/* robot.forward_kinematics(q[m,ndof]) -> poses[m,7] = [x y z qw qx qy qz]  (ikflow_solver.py:114) */
+int ikf_forward_kinematics(IkfRobot* robot, const float* q, float* poses_out, int m, void* stream);
+
+/* robot.clamp_to_joint_limits(q) in place (ikflow_solver.py:102) */
+int ikf_clamp_to_joint_limits(IkfRobot* robot, float* q, int m, void* stream);
+
+/* robot.inverse_kinematics_step_levenburg_marquardt(target_poses, q) (ikflow_solver.py:205,208):
+ * J = jacobian(q); e = [rpy(q_t (x) q_cur^-1); p_t - p_cur]; dq = solve(J^T J + lambd I, J^T e); q' = clamp(q + dq).
+ * Sample i uses pose row (i % pose_rows).  q_out may alias q_in. */
+int ikf_lm_step(IkfRobot* robot, const float* poses, int pose_rows, const float* q_in, float* q_out, int m,
+                float lambd, int clamp, void* stream);
+
+/* IKFlowSolver._calculate_pose_error (ikflow_solver.py:112-117): L2 position error and quaternion geodesic. */
+int ikf_pose_error(IkfRobot* robot, const float* q, const float* poses, int pose_rows, float* pos_err, float* rot_err,
+                   int m, void* stream);
+
+/* The LM / select / compact loop of _generate_exact_ik_solutions (ikflow_solver.py:197-233), device-side:
+ *   q_seeds   [repeat_count * n][ndof]  flow samples, row k*n + p = repeat k of pose p (ikflow_solver.py:185); updated
+ *             in place (each row holds its iterate at the first step it became valid, or after n_steps)
+ *   poses     [n][7]
+ *   final_q   [n][ndof], final_valid [n] (uint8): for every pose the LAST valid repeat at the FIRST step where any
+ *             repeat is valid (the overwrite order of the Python loop at :217-222); rows of unsolved poses are 0
+ *   n_valid_dev  optional device int32: number of solved poses
+ */
+int ikf_lm_refine(IkfRobot* robot, const float* poses, float* q_seeds, int n, int repeat_count, int n_steps,
+                  float pos_thr, float rot_thr, float lambd, float* final_q, uint8_t* final_valid,
+                  int32_t* n_valid_dev, void* stream);
+
+/* evaluate_solutions minus self-collision (ikflow/evaluation_utils.py:65-112,130-147): pose errors + joint-limit flag */
+int ikf_evaluate_solutions(IkfRobot* robot, const float* q, const float* poses, int pose_rows, float* pos_err,
+                           float* rot_err, uint8_t* limits_exceeded, int m, void* stream);
+
+/* ---- misc -------------------------------------------------------------------------------------------------------- */
+const char* ikf_last_error(void);
+const char* ikf_version(void);
+/* Number of kernels this library has launched in this process (for bench.py's gpu_launches claim). */
+uint64_t ikf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IKFLOW_B200_H_ */
