@@ -79,6 +79,8 @@ struct FlowParams {
   uint32_t* part_flag;  // [slot][2][NT]
   uint32_t* status;     // [0] status bits, [1] id of the launch that aborted
   uint32_t epoch;       // sequence numbers of this launch start at epoch + 1
+  unsigned long long* trace;  // debug: [cta < NT][layer][16] globaltimer stamps of team 0 (NULL = off)
+  int trace_layers;
   const float* in;
   const float* cond;
   float* out;
@@ -176,7 +178,10 @@ __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t expecte
   uint32_t spins = 0;
   long long t0 = 0;
   while (true) {
-    if ((int32_t)(ld_acquire(flag) - expected) >= 0) return;
+    if ((int32_t)(ld_relaxed(flag) - expected) >= 0) {
+      __threadfence();  // acquire
+      return;
+    }
     ++spins;
     if (spins == 32) t0 = clock64();
     if (spins > 32) {
@@ -190,6 +195,14 @@ __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t expecte
         }
       }
     }
+  }
+}
+
+__device__ __forceinline__ void trace_ev(const FlowParams& p, int layer, int ev) {
+  if (p.trace != nullptr && blockIdx.x < p.NT && layer < p.trace_layers) {
+    unsigned long long tns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+    p.trace[((size_t)blockIdx.x * p.trace_layers + layer) * 16 + ev] = tns;
   }
 }
 
@@ -260,48 +273,119 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
 
   if (warp == kLoaderWarp) {
     // ===== loader: bulk-TMA producer for the small-parameter blocks and the weight/activation ring =====
-    if (lane == 0) {
-      uint32_t ring_pos = 0;
-      uint32_t act_w[2] = {0, 0};  // writes so far into each activation scratch buffer
-      uint32_t xchg = 0;           // activation exchanges so far
-      auto prefetch_small = [&](int g) {
-        if (g >= total_steps) return;
-        const int b = g & 1;
-        if (g >= 2) mbar_wait(&sm.small_empty[b], ((g >> 1) - 1) & 1);
+    // The whole warp polls (lane c watches the flag of chunk c, relaxed loads, one acquire fence per batch of newly
+    // ready chunks); lane 0 issues the copies.  Weight chunks are issued as soon as their stage is free, the
+    // activation chunk of a stage follows when its producer has published it -- in the fixed order c = t, t+1, ...
+    // so that the fp32 accumulation order (and therefore the result) never depends on timing.
+    uint32_t ring_pos = 0;
+    uint32_t act_w[2] = {0, 0};  // writes so far into each activation scratch buffer
+    uint32_t xchg = 0;           // activation exchanges so far
+    auto prefetch_small = [&](int g) {
+      if (g >= total_steps) return;
+      const int b = g & 1;
+      if (g >= 2) mbar_wait(&sm.small_empty[b], ((g >> 1) - 1) & 1);
+      if (lane == 0) {
         const int in_rg = g % steps_per_rg;
         const int blk = p.block_first - in_rg / 2;
         const int n = 2 * blk + (in_rg & 1);
         mbar_arrive_expect_tx(&sm.small_full[b], kSmallBytes);
         bulk_g2s(sm.small[b], p.small + ((size_t)n * NT + t) * kSmallFloats, kSmallBytes, &sm.small_full[b]);
-      };
-      prefetch_small(0);
-      for (int g = 0; g < total_steps; ++g) {
-        const int in_rg = g % steps_per_rg;
-        const int blk = p.block_first - in_rg / 2;
-        const int n = 2 * blk + (in_rg & 1);
-        if (p.n_big == 0) prefetch_small(g + 1);
-        for (int l = 0; l < p.n_big; ++l) {
-          // input of hidden layer l = exchange number xchg (written by the previous layer of every team member)
-          const int buf = xchg & 1;
-          const uint32_t expected = p.epoch + 1 + act_w[buf];
-          const __nv_bfloat16* wbase = p.big_w + (((size_t)n * p.n_big + l) * NT + t) * NT * 2 * kTileElems;
-          const __nv_bfloat16* abase = act_slot + (size_t)buf * NT * 2 * kTileElems;
-          for (int i = 0; i < NT; ++i) {
-            const int c = (t + i) % NT;
-            const int s = ring_pos % kStages;
-            const uint32_t use = ring_pos / kStages;
-            if (use > 0) mbar_wait(&sm.empty[s], (use - 1) & 1);
-            mbar_arrive_expect_tx(&sm.full[s], kStageBytes);
-            bulk_g2s(sm.ring[s] + kChunkBytes, wbase + (size_t)c * 2 * kTileElems, kChunkBytes, &sm.full[s]);
-            wait_flag(aflag + buf * NT + c, expected, p.status, launch_id);
-            fence_proxy_async();
-            bulk_g2s(sm.ring[s], abase + (size_t)c * 2 * kTileElems, kChunkBytes, &sm.full[s]);
-            ++ring_pos;
-            if (l == 0 && i == 0) prefetch_small(g + 1);
+      }
+      __syncwarp();
+    };
+    prefetch_small(0);
+    for (int g = 0; g < total_steps; ++g) {
+      const int in_rg = g % steps_per_rg;
+      const int blk = p.block_first - in_rg / 2;
+      const int n = 2 * blk + (in_rg & 1);
+      if (p.n_big == 0) prefetch_small(g + 1);
+      for (int l = 0; l < p.n_big; ++l) {
+        // input of hidden layer l = exchange number xchg (written by the previous layer of every team member)
+        const int buf = xchg & 1;
+        const uint32_t expected = p.epoch + 1 + act_w[buf];
+        const __nv_bfloat16* wbase = p.big_w + (((size_t)n * p.n_big + l) * NT + t) * NT * 2 * kTileElems;
+        const __nv_bfloat16* abase = act_slot + (size_t)buf * NT * 2 * kTileElems;
+        const uint32_t* my_flag = aflag + buf * NT + (lane < NT ? lane : 0);
+        uint32_t ready = 0;  // bit c: chunk c has been published (warp-uniform)
+        int issued_w = 0, issued_a = 0;
+        bool gave_up = false;
+        uint32_t spins = 0;
+        long long t0 = 0;
+        while (issued_a < NT) {
+          // 1) weight chunks into every free stage
+          while (issued_w < NT) {
+            const uint32_t pos = ring_pos + issued_w;
+            const int s = pos % kStages;
+            const uint32_t use = pos / kStages;
+            int free_ = 1;
+            if (use > 0) {
+              if (lane == 0) free_ = mbar_try_wait(&sm.empty[s], (use - 1) & 1) ? 1 : 0;
+              free_ = __shfl_sync(0xffffffffu, free_, 0);
+            }
+            if (!free_) break;
+            if (lane == 0) {
+              const int c = (t + issued_w) % NT;
+              mbar_arrive_expect_tx(&sm.full[s], kStageBytes);
+              bulk_g2s(sm.ring[s] + kChunkBytes, wbase + (size_t)c * 2 * kTileElems, kChunkBytes, &sm.full[s]);
+              if (issued_w == 0) trace_ev(p, g * 4 + l, 0);
+            }
+            ++issued_w;
           }
-          ++act_w[buf];
-          ++xchg;
+          // 2) poll the flags that are still outstanding
+          if (!gave_up) {
+            bool ok = false;
+            if (lane < NT && !((ready >> lane) & 1u)) ok = (int32_t)(ld_relaxed(my_flag) - expected) >= 0;
+            ready |= __ballot_sync(0xffffffffu, ok);
+          }
+          // 3) activation chunks, in order, for stages whose weight copy is already in flight
+          int n_go = 0;
+          while (issued_a + n_go < issued_w && ((ready >> ((t + issued_a + n_go) % NT)) & 1u)) ++n_go;
+          if (n_go > 0) {
+            __threadfence();  // acquire: the relaxed flag reads above happen-before the copies below
+            fence_proxy_async();
+            if (lane == 0) {
+              for (int k = 0; k < n_go; ++k) {
+                const int c = (t + issued_a + k) % NT;
+                const int s = (ring_pos + issued_a + k) % kStages;
+                bulk_g2s(sm.ring[s], abase + (size_t)c * 2 * kTileElems, kChunkBytes, &sm.full[s]);
+              }
+            }
+            __syncwarp();
+            const bool first = issued_a == 0;
+            if (lane == 0) {
+              if (first) trace_ev(p, g * 4 + l, 1);
+              if (issued_a + n_go == NT) trace_ev(p, g * 4 + l, 2);
+            }
+            issued_a += n_go;
+            spins = 0;
+            if (l == 0 && first) prefetch_small(g + 1);
+          } else {
+            // nothing to do yet: back off a little; give up after about a second (see wait_flag)
+            ++spins;
+            if (spins == 64) t0 = clock64();
+            if (spins > 64) {
+              __nanosleep(20);
+              if ((spins & 255u) == 0 && !gave_up) {
+                int bail = 0;
+                if (lane == 0) {
+                  if (ld_relaxed(p.status + 1) == launch_id) bail = 1;
+                  else if (clock64() - t0 > 2500000000LL) {
+                    atomicOr(p.status, IKF_STATUS_SYNC_TIMEOUT);
+                    atomicExch(p.status + 1, launch_id);
+                    bail = 1;
+                  }
+                }
+                if (__shfl_sync(0xffffffffu, bail, 0)) {
+                  gave_up = true;
+                  ready = 0xffffffffu;
+                }
+              }
+            }
+          }
         }
+        ring_pos += NT;
+        ++act_w[buf];
+        ++xchg;
       }
     }
   } else if (warp == kStorerWarp) {
@@ -314,11 +398,14 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
         bar_staged_sync();  // compute warps have written + proxy-fenced the staging buffer
         if (lane == 0) {
           __nv_bfloat16* dst = act_slot + ((size_t)buf * NT + t) * 2 * kTileElems;
+          trace_ev(p, g * 4 + l, 3);
           bulk_s2g(dst, sm.staging, kChunkBytes);
           bulk_commit();
           bulk_wait_all();
+          trace_ev(p, g * 4 + l, 4);
           fence_proxy_async();
           st_release(aflag + buf * NT + t, p.epoch + 1 + act_w[buf]);
+          trace_ev(p, g * 4 + l, 5);
           mbar_arrive(&sm.staging_free);
         }
         __syncwarp();
@@ -411,9 +498,11 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
                 for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
                   for (int e = 0; e < 4; ++e) acc[mi][ni][e] = 0.f;
+              if (tid == 0) trace_ev(p, g * 4 + l - 1, 6);
               for (int i = 0; i < NT; ++i) {
                 const int s = ring_pos % kStages;
                 mbar_wait(&sm.full[s], (ring_pos / kStages) & 1);
+                if (tid == 0 && i == 0) trace_ev(p, g * 4 + l - 1, 7);
                 const uint32_t a_hi = smem_u32(sm.ring[s]);
                 const uint32_t a_lo = a_hi + kTileElems * 2;
                 const uint32_t w_hi = a_hi + kChunkBytes;
@@ -452,6 +541,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
                 if (lane == 0) mbar_arrive(&sm.empty[s]);
                 ++ring_pos;
               }
+              if (tid == 0) trace_ev(p, g * 4 + l - 1, 8);
               // ---- split-k reduction through the fp32 tile ----
               const int gq = lane >> 2, tq = lane & 3;
               if (group == 0) {
@@ -501,6 +591,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
                 v[8 * h + 7] = leaky(x1.w + b8[7]);
               }
               bar_compute();  // the tile is free for the next layer's reduction
+              if (tid == 0) trace_ev(p, g * 4 + l - 1, 9);
             }
 
             if (l < p.n_big) {
@@ -524,11 +615,13 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
               }
               fence_proxy_async();
               bar_staged_arrive();
+              if (tid == 0) trace_ev(p, g * 4 + l, 10);
               ++staged;
             }
           }
 
           // ---- last layer: this CTA's 64 features of every output, in fp32 from the activations ----
+          if (tid == 0) trace_ev(p, g * 4 + 3, 11);
           const int pb = pxchg & 1;
           {
             float po[16];
@@ -570,6 +663,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
             for (int c = lane; c < NT; c += 32) wait_flag(pflag + pb * NT + c, pexp, p.status, launch_id);
           }
           bar_compute();
+          if (tid == 0) trace_ev(p, g * 4 + 3, 12);
           {
             // fixed summation order over the team: every CTA obtains bitwise identical coefficients
             const float4 b4 = *reinterpret_cast<const float4*>(sp + kSmallLastB + 4 * eq);
@@ -598,6 +692,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
             sm.u[r][tg_off + j] = (sm.u[r][tg_off + j] - tr) * expf(-sc);
           }
           bar_compute();
+          if (tid == 0) trace_ev(p, g * 4 + 3, 13);
         }
         // ---- PermuteRandom reverse: u = u[:, perm_inv] ----
         {
@@ -694,6 +789,8 @@ struct IkfFlow {
   ikf::FlowParams base;  // pointers + model constants; per-call fields filled at launch
   uint32_t epoch = 1;  // doubles as launch id; 0 is "no launch aborted"
   int last_grid = 0;
+  unsigned long long* trace = nullptr;
+  int trace_layers = 0;
   size_t smem_bytes = 0;
 };
 
@@ -917,6 +1014,8 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   p.n_rowgroups = (batch + kRT - 1) / kRT;
   p.slots = std::min(p.n_rowgroups, flow->slots_max);
   p.epoch = flow->epoch;
+  p.trace = flow->trace;
+  p.trace_layers = flow->trace_layers;
   // every flag of this launch stays below epoch + 1 + (row groups per slot) * (subnets) * (exchanges per subnet)
   const uint32_t rg_per_slot = (uint32_t)((p.n_rowgroups + p.slots - 1) / p.slots);
   flow->epoch += rg_per_slot * 2u * (uint32_t)(block_first - block_last + 1) * (uint32_t)(flow->n_big + 1) + 2u;
@@ -957,6 +1056,13 @@ int ikf_flow_status(IkfFlow* flow, void* stream, uint32_t* status_out) {
   IKF_CUDA(cudaMemsetAsync(flow->base.status, 0, sizeof(uint32_t), (cudaStream_t)stream));
   IKF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   *status_out = host[0];
+  return IKF_OK;
+}
+
+int ikf_flow_debug_trace(IkfFlow* flow, unsigned long long* dev_stamps, int n_layers) {
+  if (!flow || n_layers < 0) return fail(IKF_EINVAL, "ikf_flow_debug_trace: bad arguments");
+  flow->trace = n_layers > 0 ? dev_stamps : nullptr;
+  flow->trace_layers = n_layers;
   return IKF_OK;
 }
 
