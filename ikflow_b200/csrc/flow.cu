@@ -35,21 +35,20 @@
 
 namespace ikf {
 
-constexpr int kRT = 64;               // rows per row group
-constexpr int kFT = 64;               // hidden features per CTA
-constexpr int kKC = 64;               // k elements per pipeline stage
-constexpr int kTileElems = kFT * kKC;  // 4096 bf16 = 8 KB
-constexpr int kChunkBytes = 2 * kTileElems * 2;  // head + tail = 16 KB
-constexpr int kStageBytes = 2 * kChunkBytes;     // activation chunk + weight chunk = 32 KB
-constexpr int kStages = 5;
-constexpr int kComputeWarps = 8;
+constexpr int kFT = 64;                // hidden features per CTA
+constexpr int kKC = 64;                // k elements per pipeline stage
+constexpr int kRTMax = 64;             // largest row group
+constexpr int kWTileBytes = kFT * kKC * 2;      // one bf16 plane of a weight chunk: 8 KB
+constexpr int kWChunkBytes = 2 * kWTileBytes;   // head + tail: 16 KB
+constexpr int kAChunkStride = 2 * kRTMax * kKC * 2;  // bytes reserved per activation chunk in the scratch ring: 16 KB
+constexpr int kComputeWarps = 4;
 constexpr int kComputeThreads = kComputeWarps * 32;
 constexpr int kLoaderWarp = kComputeWarps;
 constexpr int kStorerWarp = kComputeWarps + 1;
 constexpr int kThreads = (kComputeWarps + 2) * 32;
-constexpr int kPad = 16;      // padded width of state / condition / small-layer dimensions
-constexpr int kMaxBig = 3;    // hidden x hidden layers per subnet (coeff_fn_config - 1)
-constexpr int kHStride = 72;  // floats per row of the fp32 reduction tile
+constexpr int kCtasPerSm = 2;  // two teams share every SM: one computes while the other waits on an exchange
+constexpr int kPad = 16;       // padded width of state / small-layer dimensions
+constexpr int kMaxBig = 3;     // hidden x hidden layers per subnet (coeff_fn_config - 1)
 // per (subnet, feature tile) block of small fp32 parameters, one bulk copy:
 //   first_wT [16 k][64 f] | first_b [64] | big_b [kMaxBig][64] | last_w [16 o][64 f] | last_b [16]
 constexpr int kSmallFirstW = 0;
@@ -73,8 +72,8 @@ struct FlowParams {
   const float* flt_b;          // [kPad]
   const float* lo;             // [kPad] joint limits
   const float* hi;
-  __nv_bfloat16* act;   // [slot][2][NT c][head|tail][64 r][64 k] swizzled
-  float* partial;       // [slot][2][NT t][64 r][16 o]
+  uint8_t* act;         // [slot][2][NT c][kAChunkStride]: head [RT][64 k] then tail, swizzled
+  float* partial;       // [slot][2][NT t][kRTMax r][16 o]
   uint32_t* act_flag;   // [slot][2][NT]
   uint32_t* part_flag;  // [slot][2][NT]
   uint32_t* status;     // [0] status bits, [1] id of the launch that aborted
@@ -113,6 +112,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the thread for a hardware-defined time when the phase is still open).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a kernel bug must surface as an error, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -133,17 +142,15 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32
                "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 __device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
 }
 __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
   uint32_t v;
@@ -174,18 +181,16 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
 
 // Wait until *flag has reached `expected` (wrap-safe).  Gives up (and makes every later wait of this launch give up)
 // after about a second: the results are then garbage and IKF_STATUS_SYNC_TIMEOUT is reported, but the GPU is not hung.
+// The caller issues the acquire fence.
 __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t expected, uint32_t* status, uint32_t launch_id) {
   uint32_t spins = 0;
   long long t0 = 0;
   while (true) {
-    if ((int32_t)(ld_relaxed(flag) - expected) >= 0) {
-      __threadfence();  // acquire
-      return;
-    }
+    if ((int32_t)(ld_relaxed(flag) - expected) >= 0) return;
     ++spins;
-    if (spins == 32) t0 = clock64();
-    if (spins > 32) {
-      __nanosleep(40);
+    if (spins == 64) t0 = clock64();
+    if (spins > 64) {
+      __nanosleep(20);
       if ((spins & 255u) == 0) {
         if (ld_relaxed(status + 1) == launch_id) return;
         if (clock64() - t0 > 2500000000LL) {
@@ -208,21 +213,35 @@ __device__ __forceinline__ void trace_ev(const FlowParams& p, int layer, int ev)
 
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : v * kLeakySlope; }
 
-// byte offset of element (row, k) inside an 8 KB [64][64] bf16 tile: 128-byte rows, 16-byte chunks XOR-swizzled by
+// byte offset of element (row, k) inside a [rows][64] bf16 tile: 128-byte rows, 16-byte chunks XOR-swizzled by
 // row % 8 (conflict-free ldmatrix; also the canonical K-major SWIZZLE_128B operand layout of the tensor cores)
 __device__ __host__ __forceinline__ uint32_t tile_off_bytes(int row, int k) {
   return (uint32_t)(row * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
 }
 
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+template <int RT>
+struct FlowCfg {
+  static constexpr int kMI = RT / 32;                 // m16 tiles per warp (warp tile = 16*kMI rows x 32 features)
+  static constexpr int kATileBytes = RT * kKC * 2;    // one bf16 plane of an activation chunk
+  static constexpr int kAChunkBytes = 2 * kATileBytes;
+  static constexpr int kStageBytes = kAChunkBytes + kWChunkBytes;
+  static constexpr int kStages = RT == 64 ? 2 : 3;
+};
+
+template <int RT>
 struct __align__(1024) FlowSmem {
-  uint8_t ring[kStages][kStageBytes];  // [activation head|tail][weight head|tail]
-  uint8_t staging[kChunkBytes];        // outgoing activation chunk (head|tail)
-  float htile[kRT * kHStride];         // fp32 tile for the split-k reduction
+  using C = FlowCfg<RT>;
+  uint8_t ring[C::kStages][C::kStageBytes];  // [activation head|tail][weight head|tail]
+  uint8_t staging[C::kAChunkBytes];          // outgoing activation chunk; reused as the last layer's warp partials
   float small[2][kSmallFloats];
-  float u[kRT][kPad];      // flow state
-  float cnd[kRT][kPad];    // condition (first 8 columns used)
-  float a[kRT][kPad];      // output of the last layer of the current subnet
-  uint64_t full[kStages], empty[kStages];
+  float u[RT][kPad];   // flow state
+  float cnd[RT][8];    // condition
+  float a[RT][kPad];   // output of the last layer of the current subnet
+  uint64_t full[C::kStages], empty[C::kStages];
   uint64_t small_full[2], small_empty[2];
   uint64_t staging_free;
 };
@@ -230,9 +249,14 @@ struct __align__(1024) FlowSmem {
 // ---------------------------------------------------------------------------------------------------------------------
 // the kernel
 
-__global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowParams p) {
+template <int RT>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) flow_inverse_kernel(const FlowParams p) {
+  using C = FlowCfg<RT>;
+  constexpr int MI = C::kMI;
+  constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
-  FlowSmem& sm = *reinterpret_cast<FlowSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  FlowSmem<RT>& sm =
+      *reinterpret_cast<FlowSmem<RT>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -257,8 +281,8 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
   }
   __syncthreads();
 
-  __nv_bfloat16* act_slot = p.act + (size_t)slot * 2 * NT * 2 * kTileElems;
-  float* part_slot = p.partial + (size_t)slot * 2 * NT * kRT * kPad;
+  uint8_t* act_slot = p.act + (size_t)slot * 2 * NT * kAChunkStride;
+  float* part_slot = p.partial + (size_t)slot * 2 * NT * kRTMax * kPad;
   uint32_t* aflag = p.act_flag + (size_t)slot * 2 * NT;
   uint32_t* pflag = p.part_flag + (size_t)slot * 2 * NT;
 
@@ -268,15 +292,14 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
   const int total_steps = my_rgs * steps_per_rg;
 
   // The three roles walk the same schedule: step g = (row group, block, subnet); within a step the layers in order.
-  // `writes` counts the activation exchanges so far: exchange number w uses scratch buffer w % 2 and flag value
-  // epoch + 1 + w / 2 ... kept as two explicit per-buffer counters below.
+  // Activation exchange number x uses scratch buffer x % 2; its flags carry epoch + 1 + (writes so far to that buffer).
 
   if (warp == kLoaderWarp) {
     // ===== loader: bulk-TMA producer for the small-parameter blocks and the weight/activation ring =====
-    // The whole warp polls (lane c watches the flag of chunk c, relaxed loads, one acquire fence per batch of newly
-    // ready chunks); lane 0 issues the copies.  Weight chunks are issued as soon as their stage is free, the
-    // activation chunk of a stage follows when its producer has published it -- in the fixed order c = t, t+1, ...
-    // so that the fp32 accumulation order (and therefore the result) never depends on timing.
+    // The whole warp polls (lane c watches the flag of chunk c, relaxed loads); lane 0 issues the copies.  Weight
+    // chunks are issued as soon as their stage is free, the activation chunk of a stage follows when its producer has
+    // published it -- in the fixed order c = t, t+1, ... so that the fp32 accumulation order (and therefore the
+    // result) never depends on timing.
     uint32_t ring_pos = 0;
     uint32_t act_w[2] = {0, 0};  // writes so far into each activation scratch buffer
     uint32_t xchg = 0;           // activation exchanges so far
@@ -303,59 +326,100 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
         // input of hidden layer l = exchange number xchg (written by the previous layer of every team member)
         const int buf = xchg & 1;
         const uint32_t expected = p.epoch + 1 + act_w[buf];
-        const __nv_bfloat16* wbase = p.big_w + (((size_t)n * p.n_big + l) * NT + t) * NT * 2 * kTileElems;
-        const __nv_bfloat16* abase = act_slot + (size_t)buf * NT * 2 * kTileElems;
+        const uint8_t* wbase =
+            reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n * p.n_big + l) * NT + t) * NT * kWChunkBytes;
+        const uint8_t* abase = act_slot + (size_t)buf * NT * kAChunkStride;
         const uint32_t* my_flag = aflag + buf * NT + (lane < NT ? lane : 0);
+        {
+          // The model (203 MB for Panda) does not stay in L2 between calls, so every weight byte comes from HBM once
+          // per launch; pull the NEXT hidden layer's slice of this CTA into L2 now, one whole layer ahead of its use,
+          // so that the ring refills at L2 latency instead of DRAM latency.
+          int n2 = n, l2 = l + 1;
+          if (l2 == p.n_big) {
+            l2 = 0;
+            n2 = -1;
+            if (g + 1 < total_steps) {
+              const int in_rg2 = (g + 1) % steps_per_rg;
+              n2 = 2 * (p.block_first - in_rg2 / 2) + (in_rg2 & 1);
+            }
+          }
+          if (n2 >= 0) {
+            const uint8_t* wnext =
+                reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n2 * p.n_big + l2) * NT + t) * NT * kWChunkBytes;
+            for (int k = lane; k < NT; k += 32) bulk_prefetch_l2(wnext + (size_t)((t + k) % NT) * kWChunkBytes, kWChunkBytes);
+          }
+        }
         uint32_t ready = 0;  // bit c: chunk c has been published (warp-uniform)
         int issued_w = 0, issued_a = 0;
         bool gave_up = false;
         uint32_t spins = 0;
         long long t0 = 0;
         while (issued_a < NT) {
-          // 1) weight chunks into every free stage
-          while (issued_w < NT) {
-            const uint32_t pos = ring_pos + issued_w;
-            const int s = pos % kStages;
-            const uint32_t use = pos / kStages;
-            int free_ = 1;
-            if (use > 0) {
-              if (lane == 0) free_ = mbar_try_wait(&sm.empty[s], (use - 1) & 1) ? 1 : 0;
-              free_ = __shfl_sync(0xffffffffu, free_, 0);
+          // 1) which stages are free for the next weight chunks?  lane k looks at chunk issued_w + k
+          int n_w = 0;
+          {
+            bool free_ = false;
+            if (lane < kStages && issued_w + lane < NT) {
+              const uint32_t pos = ring_pos + issued_w + lane;
+              const uint32_t use = pos / kStages;
+              free_ = use == 0 || mbar_test_wait(&sm.empty[pos % kStages], (use - 1) & 1);
             }
-            if (!free_) break;
-            if (lane == 0) {
-              const int c = (t + issued_w) % NT;
-              mbar_arrive_expect_tx(&sm.full[s], kStageBytes);
-              bulk_g2s(sm.ring[s] + kChunkBytes, wbase + (size_t)c * 2 * kTileElems, kChunkBytes, &sm.full[s]);
-              if (issued_w == 0) trace_ev(p, g * 4 + l, 0);
-            }
-            ++issued_w;
+            const uint32_t m = __ballot_sync(0xffffffffu, free_);
+            n_w = __ffs(~m) - 1;  // consecutive free stages starting at chunk issued_w
           }
           // 2) poll the flags that are still outstanding
-          if (!gave_up) {
+          if (!gave_up && ready != 0xffffffffu) {
             bool ok = false;
             if (lane < NT && !((ready >> lane) & 1u)) ok = (int32_t)(ld_relaxed(my_flag) - expected) >= 0;
             ready |= __ballot_sync(0xffffffffu, ok);
+            if (__popc(ready) == NT) ready = 0xffffffffu;
           }
-          // 3) activation chunks, in order, for stages whose weight copy is already in flight
+          // 3) activation chunks, in order, for stages whose weight copy is (being) issued
           int n_go = 0;
-          while (issued_a + n_go < issued_w && ((ready >> ((t + issued_a + n_go) % NT)) & 1u)) ++n_go;
-          if (n_go > 0) {
-            __threadfence();  // acquire: the relaxed flag reads above happen-before the copies below
-            fence_proxy_async();
-            if (lane == 0) {
-              for (int k = 0; k < n_go; ++k) {
-                const int c = (t + issued_a + k) % NT;
-                const int s = (ring_pos + issued_a + k) % kStages;
-                bulk_g2s(sm.ring[s], abase + (size_t)c * 2 * kTileElems, kChunkBytes, &sm.full[s]);
-              }
+          while (n_go < kStages && issued_a + n_go < issued_w + n_w && ((ready >> ((t + issued_a + n_go) % NT)) & 1u))
+            ++n_go;
+          if (n_w > 0 || n_go > 0) {
+            // One bulk copy keeps its issuing thread busy for ~0.4 us whatever its size, but copies issued by
+            // different lanes run concurrently (measured: scripts/ubench/ingest2.cu) -- so every pending copy gets
+            // its own lane and all of them go out in one instruction: lanes 0.. the weight chunks, lanes 8.. the
+            // activation chunks.
+            const bool do_w = lane < n_w;
+            const bool do_a = lane >= 8 && lane < 8 + n_go;
+            void* dst = nullptr;
+            const void* src = nullptr;
+            uint32_t bytes = 0;
+            uint64_t* bar = nullptr;
+            if (do_w) {
+              const int iw = issued_w + lane;
+              const int st = (ring_pos + iw) % kStages;
+              mbar_arrive_expect_tx(&sm.full[st], C::kStageBytes);
+              dst = sm.ring[st] + C::kAChunkBytes;
+              src = wbase + (size_t)((t + iw) % NT) * kWChunkBytes;
+              bytes = kWChunkBytes;
+              bar = &sm.full[st];
+            }
+            if (do_a) {
+              const int ia = issued_a + (lane - 8);
+              const int st = (ring_pos + ia) % kStages;
+              dst = sm.ring[st];
+              src = abase + (size_t)((t + ia) % NT) * kAChunkStride;
+              bytes = C::kAChunkBytes;
+              bar = &sm.full[st];
             }
             __syncwarp();
-            const bool first = issued_a == 0;
+            // The activation chunks were written by bulk stores (async proxy) that completed before their flag was
+            // released and are read here by bulk copies from L2 (no L1 in the path): a proxy fence orders the copies
+            // after the flag reads.
+            if (n_go > 0) fence_proxy_async();
+            if (do_w || do_a) bulk_g2s(dst, src, bytes, bar);
+            __syncwarp();
             if (lane == 0) {
-              if (first) trace_ev(p, g * 4 + l, 1);
+              if (issued_w == 0 && n_w > 0) trace_ev(p, g * 4 + l, 0);
+              if (issued_a == 0 && n_go > 0) trace_ev(p, g * 4 + l, 1);
               if (issued_a + n_go == NT) trace_ev(p, g * 4 + l, 2);
             }
+            const bool first = issued_a == 0 && n_go > 0;
+            issued_w += n_w;
             issued_a += n_go;
             spins = 0;
             if (l == 0 && first) prefetch_small(g + 1);
@@ -397,13 +461,12 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
         const int buf = xchg & 1;
         bar_staged_sync();  // compute warps have written + proxy-fenced the staging buffer
         if (lane == 0) {
-          __nv_bfloat16* dst = act_slot + ((size_t)buf * NT + t) * 2 * kTileElems;
+          uint8_t* dst = act_slot + ((size_t)buf * NT + t) * kAChunkStride;
           trace_ev(p, g * 4 + l, 3);
-          bulk_s2g(dst, sm.staging, kChunkBytes);
+          bulk_s2g(dst, sm.staging, C::kAChunkBytes);
           bulk_commit();
           bulk_wait_all();
           trace_ev(p, g * 4 + l, 4);
-          fence_proxy_async();
           st_release(aflag + buf * NT + t, p.epoch + 1 + act_w[buf]);
           trace_ev(p, g * 4 + l, 5);
           mbar_arrive(&sm.staging_free);
@@ -414,12 +477,12 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
       }
     }
   } else {
-    // ===== compute warps =====
-    const int group = warp >> 2;         // split-k half
-    const int warp_m = (warp & 3) >> 1;  // 32-row half of the tile
-    const int warp_n = warp & 1;         // 32-feature half of the tile
-    const int erow = tid >> 2;           // epilogue mapping: row, and 16-byte column groups eq and eq + 4
-    const int eq = tid & 3;
+    // ===== compute warps: 2 x 2 over the RT x 64 tile, warp tile (RT/2) rows x 32 features =====
+    const int warp_m = warp >> 1;
+    const int warp_n = warp & 1;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int row_base = warp_m * (16 * MI);  // + mi * 16 + gq (+ 8)
+    const int col_base = warp_n * 32;         // + ni * 8 + 2 * tq (+ 1)
     uint32_t ring_pos = 0;
     uint32_t part_w[2] = {0, 0};
     uint32_t pxchg = 0;
@@ -434,16 +497,16 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
     int g = 0;
     for (int rg = slot; rg < p.n_rowgroups; rg += p.slots) {
       // ---- load the flow state and the condition of this row group ----
-      for (int i = tid; i < kRT * kPad; i += kComputeThreads) {
+      for (int i = tid; i < RT * kPad; i += kComputeThreads) {
         const int r = i / kPad, j = i % kPad;
-        const int row = rg * kRT + r;
+        const int row = rg * RT + r;
         float uv = 0.f, cv = 0.f;
         if (row < p.batch) {
           if (j < p.W) uv = p.in[(size_t)row * p.in_ld + j];
           if (j < p.cond_cols) cv = p.cond[(size_t)(row % p.cond_rows) * p.cond_ld + j];
         }
         sm.u[r][j] = uv;
-        sm.cnd[r][j] = cv;
+        if (j < 8) sm.cnd[r][j] = cv;
       }
       bar_compute();
 
@@ -458,83 +521,99 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
           const int tg_off = sidx == 0 ? p.s1 : 0;
           const int tg_len = sidx == 0 ? p.s2 : p.s1;
 
-          float v[16];  // activations of (erow, features 8eq..8eq+7 and 32+8eq..32+8eq+7) after bias + LeakyReLU
+          // v[mi][ni][e]: activation (after bias + LeakyReLU) of row row_base + mi*16 + gq + 8*(e>>1),
+          //               feature col_base + ni*8 + 2*tq + (e&1)  -- the mma accumulator fragment layout
+          float v[MI][4][4];
+
           // ---- first layer: fp32 SIMT from the replicated state ----
           {
-            float acc[16];
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+            for (int ni = 0; ni < 4; ++ni) {
+              const float2 b2 = *reinterpret_cast<const float2*>(sp + kSmallFirstB + col_base + ni * 8 + 2 * tq);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) acc[8 * h + e] = sp[kSmallFirstB + 32 * h + 8 * eq + e];
+              for (int mi = 0; mi < MI; ++mi) {
+                v[mi][ni][0] = b2.x;
+                v[mi][ni][1] = b2.y;
+                v[mi][ni][2] = b2.x;
+                v[mi][ni][3] = b2.y;
+              }
+            }
             const int kin = in_len + p.dim_cond;
             for (int k = 0; k < kin; ++k) {
-              const float x = k < in_len ? sm.u[erow][in_off + k] : sm.cnd[erow][k - in_len];
-              const float* wr = sp + kSmallFirstW + k * kFT;
+              float x[MI][2];
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const float4 w0 = *reinterpret_cast<const float4*>(wr + 32 * h + 8 * eq);
-                const float4 w1 = *reinterpret_cast<const float4*>(wr + 32 * h + 8 * eq + 4);
-                acc[8 * h + 0] = fmaf(x, w0.x, acc[8 * h + 0]);
-                acc[8 * h + 1] = fmaf(x, w0.y, acc[8 * h + 1]);
-                acc[8 * h + 2] = fmaf(x, w0.z, acc[8 * h + 2]);
-                acc[8 * h + 3] = fmaf(x, w0.w, acc[8 * h + 3]);
-                acc[8 * h + 4] = fmaf(x, w1.x, acc[8 * h + 4]);
-                acc[8 * h + 5] = fmaf(x, w1.y, acc[8 * h + 5]);
-                acc[8 * h + 6] = fmaf(x, w1.z, acc[8 * h + 6]);
-                acc[8 * h + 7] = fmaf(x, w1.w, acc[8 * h + 7]);
+              for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const int r = row_base + mi * 16 + gq + 8 * h;
+                  x[mi][h] = k < in_len ? sm.u[r][in_off + k] : sm.cnd[r][k - in_len];
+                }
+              const float* wr = sp + kSmallFirstW + k * kFT + col_base + 2 * tq;
+#pragma unroll
+              for (int ni = 0; ni < 4; ++ni) {
+                const float2 w2 = *reinterpret_cast<const float2*>(wr + ni * 8);
+#pragma unroll
+                for (int mi = 0; mi < MI; ++mi) {
+                  v[mi][ni][0] = fmaf(x[mi][0], w2.x, v[mi][ni][0]);
+                  v[mi][ni][1] = fmaf(x[mi][0], w2.y, v[mi][ni][1]);
+                  v[mi][ni][2] = fmaf(x[mi][1], w2.x, v[mi][ni][2]);
+                  v[mi][ni][3] = fmaf(x[mi][1], w2.y, v[mi][ni][3]);
+                }
               }
             }
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = leaky(acc[e]);
+            for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+              for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[mi][ni][e] = leaky(v[mi][ni][e]);
           }
 
           for (int l = 0; l <= p.n_big; ++l) {
             if (l > 0) {
               // ---- hidden layer l-1: bf16x3 tensor-core tiles over the NT k-chunks ----
-              float acc[2][4][4];
 #pragma unroll
-              for (int mi = 0; mi < 2; ++mi)
+              for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) acc[mi][ni][e] = 0.f;
+                  for (int e = 0; e < 4; ++e) v[mi][ni][e] = 0.f;
               if (tid == 0) trace_ev(p, g * 4 + l - 1, 6);
               for (int i = 0; i < NT; ++i) {
                 const int s = ring_pos % kStages;
                 mbar_wait(&sm.full[s], (ring_pos / kStages) & 1);
                 if (tid == 0 && i == 0) trace_ev(p, g * 4 + l - 1, 7);
                 const uint32_t a_hi = smem_u32(sm.ring[s]);
-                const uint32_t a_lo = a_hi + kTileElems * 2;
-                const uint32_t w_hi = a_hi + kChunkBytes;
-                const uint32_t w_lo = w_hi + kTileElems * 2;
+                const uint32_t a_lo = a_hi + C::kATileBytes;
+                const uint32_t w_hi = a_hi + C::kAChunkBytes;
+                const uint32_t w_lo = w_hi + kWTileBytes;
 #pragma unroll
-                for (int kk2 = 0; kk2 < 2; ++kk2) {
-                  const int kk = group * 2 + kk2;  // k16 step inside the 64-wide chunk
-                  uint32_t ah[2][4], al[2][4], bh[2][4], bl[2][4];
+                for (int kk = 0; kk < kKC / 16; ++kk) {
+                  uint32_t ah[MI][4], al[MI][4], bh[2][4], bl[2][4];
 #pragma unroll
-                  for (int mi = 0; mi < 2; ++mi) {
-                    const int row = warp_m * 32 + mi * 16 + a_row_in;
+                  for (int mi = 0; mi < MI; ++mi) {
+                    const int row = row_base + mi * 16 + a_row_in;
                     const uint32_t off = row * 128 + ((((kk * 2 + a_kc) ^ (row & 7)) & 7) << 4);
                     ldsm_x4(a_hi + off, ah[mi]);
                     ldsm_x4(a_lo + off, al[mi]);
                   }
 #pragma unroll
                   for (int nj = 0; nj < 2; ++nj) {
-                    const int row = warp_n * 32 + nj * 16 + b_row_in;
+                    const int row = col_base + nj * 16 + b_row_in;
                     const uint32_t off = row * 128 + ((((kk * 2 + b_kc) ^ (row & 7)) & 7) << 4);
                     ldsm_x4(w_hi + off, bh[nj]);
                     ldsm_x4(w_lo + off, bl[nj]);
                   }
 #pragma unroll
-                  for (int mi = 0; mi < 2; ++mi)
+                  for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni) {
                       const int nj = ni >> 1, o = (ni & 1) * 2;
                       if (p.precision == IKF_PRECISION_BF16X3) {
-                        mma_bf16(acc[mi][ni], al[mi], bh[nj][o], bh[nj][o + 1]);
-                        mma_bf16(acc[mi][ni], ah[mi], bl[nj][o], bl[nj][o + 1]);
+                        mma_bf16(v[mi][ni], al[mi], bh[nj][o], bh[nj][o + 1]);
+                        mma_bf16(v[mi][ni], ah[mi], bl[nj][o], bl[nj][o + 1]);
                       }
-                      mma_bf16(acc[mi][ni], ah[mi], bh[nj][o], bh[nj][o + 1]);
+                      mma_bf16(v[mi][ni], ah[mi], bh[nj][o], bh[nj][o + 1]);
                     }
                 }
                 __syncwarp();
@@ -542,77 +621,37 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
                 ++ring_pos;
               }
               if (tid == 0) trace_ev(p, g * 4 + l - 1, 8);
-              // ---- split-k reduction through the fp32 tile ----
-              const int gq = lane >> 2, tq = lane & 3;
-              if (group == 0) {
+              const float* bb = sp + kSmallBigB + (l - 1) * kFT + col_base + 2 * tq;
 #pragma unroll
-                for (int mi = 0; mi < 2; ++mi)
+              for (int ni = 0; ni < 4; ++ni) {
+                const float2 b2 = *reinterpret_cast<const float2*>(bb + ni * 8);
 #pragma unroll
-                  for (int ni = 0; ni < 4; ++ni) {
-                    const int r0 = warp_m * 32 + mi * 16 + gq, c0 = warp_n * 32 + ni * 8 + 2 * tq;
-                    *reinterpret_cast<float2*>(&sm.htile[r0 * kHStride + c0]) =
-                        make_float2(acc[mi][ni][0], acc[mi][ni][1]);
-                    *reinterpret_cast<float2*>(&sm.htile[(r0 + 8) * kHStride + c0]) =
-                        make_float2(acc[mi][ni][2], acc[mi][ni][3]);
-                  }
+                for (int mi = 0; mi < MI; ++mi) {
+                  v[mi][ni][0] = leaky(v[mi][ni][0] + b2.x);
+                  v[mi][ni][1] = leaky(v[mi][ni][1] + b2.y);
+                  v[mi][ni][2] = leaky(v[mi][ni][2] + b2.x);
+                  v[mi][ni][3] = leaky(v[mi][ni][3] + b2.y);
+                }
               }
-              bar_compute();
-              if (group == 1) {
-#pragma unroll
-                for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-                  for (int ni = 0; ni < 4; ++ni) {
-                    const int r0 = warp_m * 32 + mi * 16 + gq, c0 = warp_n * 32 + ni * 8 + 2 * tq;
-                    float2* p0 = reinterpret_cast<float2*>(&sm.htile[r0 * kHStride + c0]);
-                    float2* p1 = reinterpret_cast<float2*>(&sm.htile[(r0 + 8) * kHStride + c0]);
-                    float2 x0 = *p0, x1 = *p1;
-                    x0.x += acc[mi][ni][0];
-                    x0.y += acc[mi][ni][1];
-                    x1.x += acc[mi][ni][2];
-                    x1.y += acc[mi][ni][3];
-                    *p0 = x0;
-                    *p1 = x1;
-                  }
-              }
-              bar_compute();
-              const float* bb = sp + kSmallBigB + (l - 1) * kFT;
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const float4 x0 = *reinterpret_cast<const float4*>(&sm.htile[erow * kHStride + 32 * h + 8 * eq]);
-                const float4 x1 = *reinterpret_cast<const float4*>(&sm.htile[erow * kHStride + 32 * h + 8 * eq + 4]);
-                const float* b8 = bb + 32 * h + 8 * eq;
-                v[8 * h + 0] = leaky(x0.x + b8[0]);
-                v[8 * h + 1] = leaky(x0.y + b8[1]);
-                v[8 * h + 2] = leaky(x0.z + b8[2]);
-                v[8 * h + 3] = leaky(x0.w + b8[3]);
-                v[8 * h + 4] = leaky(x1.x + b8[4]);
-                v[8 * h + 5] = leaky(x1.y + b8[5]);
-                v[8 * h + 6] = leaky(x1.z + b8[6]);
-                v[8 * h + 7] = leaky(x1.w + b8[7]);
-              }
-              bar_compute();  // the tile is free for the next layer's reduction
-              if (tid == 0) trace_ev(p, g * 4 + l - 1, 9);
             }
 
             if (l < p.n_big) {
               // ---- publish: split into bf16 head/tail, stage the swizzled chunk, hand it to the storer ----
               if (staged > 0) mbar_wait(&sm.staging_free, (staged - 1) & 1);
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                uint32_t hi[4], lo[4];
+              for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float f0 = v[8 * h + 2 * e], f1 = v[8 * h + 2 * e + 1];
-                  const __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
-                  const __nv_bfloat16 l0 = __float2bfloat16_rn(f0 - __bfloat162float(h0));
-                  const __nv_bfloat16 l1 = __float2bfloat16_rn(f1 - __bfloat162float(h1));
-                  hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                  lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                }
-                const uint32_t off = tile_off_bytes(erow, 32 * h + 8 * eq);
-                *reinterpret_cast<uint4*>(sm.staging + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(sm.staging + kTileElems * 2 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              }
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    const float f0 = v[mi][ni][2 * h], f1 = v[mi][ni][2 * h + 1];
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
+                    const __nv_bfloat16 l0 = __float2bfloat16_rn(f0 - __bfloat162float(h0));
+                    const __nv_bfloat16 l1 = __float2bfloat16_rn(f1 - __bfloat162float(h1));
+                    const uint32_t off = tile_off_bytes(row_base + mi * 16 + gq + 8 * h, col_base + ni * 8 + 2 * tq);
+                    *reinterpret_cast<uint32_t*>(sm.staging + off) = pack_bf16(h0, h1);
+                    *reinterpret_cast<uint32_t*>(sm.staging + C::kATileBytes + off) = pack_bf16(l0, l1);
+                  }
               fence_proxy_async();
               bar_staged_arrive();
               if (tid == 0) trace_ev(p, g * 4 + l, 10);
@@ -620,63 +659,85 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
             }
           }
 
-          // ---- last layer: this CTA's 64 features of every output, in fp32 from the activations ----
+          // ---- last layer: this CTA's 64 features of every output, in fp32 straight from the activations ----
           if (tid == 0) trace_ev(p, g * 4 + 3, 11);
           const int pb = pxchg & 1;
+          if (staged > 0) mbar_wait(&sm.staging_free, (staged - 1) & 1);  // the storer is done with the buffer
+          float* wpart = reinterpret_cast<float*>(sm.staging);           // [2 warp_n][RT][16]
           {
-            float po[16];
 #pragma unroll
-            for (int o = 0; o < 16; ++o) {
-              const float* wr = sp + kSmallLastW + o * kFT;
-              float s = 0.f;
+            for (int o4 = 0; o4 < 4; ++o4) {
+              float po[MI][2][4];
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const float4 w0 = *reinterpret_cast<const float4*>(wr + 32 * h + 8 * eq);
-                const float4 w1 = *reinterpret_cast<const float4*>(wr + 32 * h + 8 * eq + 4);
-                s = fmaf(v[8 * h + 0], w0.x, s);
-                s = fmaf(v[8 * h + 1], w0.y, s);
-                s = fmaf(v[8 * h + 2], w0.z, s);
-                s = fmaf(v[8 * h + 3], w0.w, s);
-                s = fmaf(v[8 * h + 4], w1.x, s);
-                s = fmaf(v[8 * h + 5], w1.y, s);
-                s = fmaf(v[8 * h + 6], w1.z, s);
-                s = fmaf(v[8 * h + 7], w1.w, s);
+              for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                  for (int oo = 0; oo < 4; ++oo) po[mi][h][oo] = 0.f;
+#pragma unroll
+              for (int oo = 0; oo < 4; ++oo) {
+                const float* wr = sp + kSmallLastW + (o4 * 4 + oo) * kFT + col_base + 2 * tq;
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                  const float2 w2 = *reinterpret_cast<const float2*>(wr + ni * 8);
+#pragma unroll
+                  for (int mi = 0; mi < MI; ++mi) {
+                    po[mi][0][oo] = fmaf(v[mi][ni][0], w2.x, po[mi][0][oo]);
+                    po[mi][0][oo] = fmaf(v[mi][ni][1], w2.y, po[mi][0][oo]);
+                    po[mi][1][oo] = fmaf(v[mi][ni][2], w2.x, po[mi][1][oo]);
+                    po[mi][1][oo] = fmaf(v[mi][ni][3], w2.y, po[mi][1][oo]);
+                  }
+                }
               }
-              s += __shfl_xor_sync(0xffffffffu, s, 1);
-              s += __shfl_xor_sync(0xffffffffu, s, 2);
-              po[o] = s;
+#pragma unroll
+              for (int mi = 0; mi < MI; ++mi)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                  for (int oo = 0; oo < 4; ++oo) {
+                    float s = po[mi][h][oo];
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    po[mi][h][oo] = s;
+                  }
+                  if (tq == o4) {
+                    const int r = row_base + mi * 16 + gq + 8 * h;
+                    *reinterpret_cast<float4*>(&wpart[(warp_n * RT + r) * kPad + 4 * o4]) =
+                        make_float4(po[mi][h][0], po[mi][h][1], po[mi][h][2], po[mi][h][3]);
+                  }
+                }
             }
-            // lane eq of the quad stores outputs 4eq..4eq+3
-            float4 mine;
-            mine.x = eq == 0 ? po[0] : eq == 1 ? po[4] : eq == 2 ? po[8] : po[12];
-            mine.y = eq == 0 ? po[1] : eq == 1 ? po[5] : eq == 2 ? po[9] : po[13];
-            mine.z = eq == 0 ? po[2] : eq == 1 ? po[6] : eq == 2 ? po[10] : po[14];
-            mine.w = eq == 0 ? po[3] : eq == 1 ? po[7] : eq == 2 ? po[11] : po[15];
-            float* dst = part_slot + (((size_t)pb * NT + t) * kRT + erow) * kPad + 4 * eq;
-            __stcg(reinterpret_cast<float4*>(dst), mine);
           }
-          __threadfence();
+          bar_compute();
+          for (int i = tid; i < RT * 4; i += kComputeThreads) {
+            const int r = i >> 2, o4 = i & 3;
+            const float4 x0 = *reinterpret_cast<const float4*>(&wpart[r * kPad + 4 * o4]);
+            const float4 x1 = *reinterpret_cast<const float4*>(&wpart[(RT + r) * kPad + 4 * o4]);
+            float* dst = part_slot + (((size_t)pb * NT + t) * kRTMax + r) * kPad + 4 * o4;
+            __stcg(reinterpret_cast<float4*>(dst), make_float4(x0.x + x1.x, x0.y + x1.y, x0.z + x1.z, x0.w + x1.w));
+          }
           bar_compute();
           const uint32_t pexp = p.epoch + 1 + part_w[pb];
-          if (tid == 0) st_release(pflag + pb * NT + t, pexp);
+          if (tid == 0) st_release(pflag + pb * NT + t, pexp);  // cumulative over the barrier: one fence per CTA
           if (warp == 0) {
             for (int c = lane; c < NT; c += 32) wait_flag(pflag + pb * NT + c, pexp, p.status, launch_id);
+            __threadfence();  // acquire
           }
           bar_compute();
           if (tid == 0) trace_ev(p, g * 4 + 3, 12);
-          {
+          for (int i = tid; i < RT * 4; i += kComputeThreads) {
             // fixed summation order over the team: every CTA obtains bitwise identical coefficients
-            const float4 b4 = *reinterpret_cast<const float4*>(sp + kSmallLastB + 4 * eq);
-            float4 s = b4;
-            const float* src = part_slot + ((size_t)pb * NT * kRT + erow) * kPad + 4 * eq;
+            const int r = i >> 2, o4 = i & 3;
+            float4 s = *reinterpret_cast<const float4*>(sp + kSmallLastB + 4 * o4);
+            const float* src = part_slot + ((size_t)pb * NT * kRTMax + r) * kPad + 4 * o4;
             for (int c = 0; c < NT; ++c) {
-              const float4 x = __ldcg(reinterpret_cast<const float4*>(src + (size_t)c * kRT * kPad));
+              const float4 x = __ldcg(reinterpret_cast<const float4*>(src + (size_t)c * kRTMax * kPad));
               s.x += x.x;
               s.y += x.y;
               s.z += x.z;
               s.w += x.w;
             }
-            *reinterpret_cast<float4*>(&sm.a[erow][4 * eq]) = s;
+            *reinterpret_cast<float4*>(&sm.a[r][4 * o4]) = s;
           }
           // this subnet's small parameters are no longer needed
           __syncwarp();
@@ -685,7 +746,7 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
           ++pxchg;
           bar_compute();
           // ---- affine coupling, reverse direction: y = (x - t) * exp(-clamp * 0.636 * atan(s)) ----
-          for (int i = tid; i < kRT * tg_len; i += kComputeThreads) {
+          for (int i = tid; i < RT * tg_len; i += kComputeThreads) {
             const int r = i / tg_len, j = i % tg_len;
             const float sc = p.clamp_scale * atanf(sm.a[r][j]);
             const float tr = sm.a[r][tg_len + j];
@@ -696,17 +757,18 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
         }
         // ---- PermuteRandom reverse: u = u[:, perm_inv] ----
         {
-          float tmp[4];
+          constexpr int kPer = (RT * kPad + kComputeThreads - 1) / kComputeThreads;
+          float tmp[kPer];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < kPer; ++c) {
             const int i = tid + c * kComputeThreads;
-            tmp[c] = i < kRT * p.W ? sm.u[i / p.W][p.perm_inv[blk * kPad + i % p.W]] : 0.f;
+            tmp[c] = i < RT * p.W ? sm.u[i / p.W][p.perm_inv[blk * kPad + i % p.W]] : 0.f;
           }
           bar_compute();
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < kPer; ++c) {
             const int i = tid + c * kComputeThreads;
-            if (i < kRT * p.W) sm.u[i / p.W][i % p.W] = tmp[c];
+            if (i < RT * p.W) sm.u[i / p.W][i % p.W] = tmp[c];
           }
           bar_compute();
         }
@@ -714,9 +776,9 @@ __global__ void __launch_bounds__(kThreads, 1) flow_inverse_kernel(const FlowPar
 
       // ---- write this row group (team member 0 only; all replicas are identical) ----
       if (t == 0) {
-        for (int i = tid; i < kRT * p.out_cols; i += kComputeThreads) {
+        for (int i = tid; i < RT * p.out_cols; i += kComputeThreads) {
           const int r = i / p.out_cols, j = i % p.out_cols;
-          const int row = rg * kRT + r;
+          const int row = rg * RT + r;
           if (row >= p.batch) continue;
           float o;
           if (p.finalize) {
@@ -787,6 +849,7 @@ struct IkfFlow {
   void* blob = nullptr;  // one device allocation holding everything below
   size_t blob_bytes = 0, big_w_bytes = 0;
   ikf::FlowParams base;  // pointers + model constants; per-call fields filled at launch
+  size_t smem32 = 0, smem64 = 0;
   uint32_t epoch = 1;  // doubles as launch id; 0 is "no launch aborted"
   int last_grid = 0;
   unsigned long long* trace = nullptr;
@@ -847,14 +910,14 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   const int n_big = desc->coeff_fn_config - 1, nb = desc->nb_nodes, n_sub = 2 * nb;
   f->NT = NT;
   f->n_big = n_big;
-  f->slots_max = std::max(1, f->num_sms / NT);
+  f->slots_max = std::max(1, kCtasPerSm * f->num_sms / NT);
   if (NT > f->num_sms) {
     delete f;
     return fail(IKF_EDEVICE, "ikf_flow_create: hidden=%d needs %d co-resident CTAs, device has %d SMs", H, NT, f->num_sms);
   }
 
   // ---- host-side repack ----
-  const size_t big_elems = (size_t)n_sub * n_big * NT * NT * 2 * kTileElems;
+  const size_t big_elems = (size_t)n_sub * n_big * NT * NT * 2 * (kFT * kKC);
   const size_t small_floats = (size_t)n_sub * NT * kSmallFloats;
   std::vector<uint16_t> big(big_elems);
   std::vector<float> small(small_floats, 0.f);
@@ -880,8 +943,8 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
         wp = b + H;
         for (int tt = 0; tt < NT; ++tt) {
           for (int c = 0; c < NT; ++c) {
-            uint16_t* hi = big.data() + ((((size_t)n * n_big + l) * NT + tt) * NT + c) * 2 * kTileElems;
-            uint16_t* lo = hi + kTileElems;
+            uint16_t* hi = big.data() + ((((size_t)n * n_big + l) * NT + tt) * NT + c) * 2 * (kFT * kKC);
+            uint16_t* lo = hi + (kFT * kKC);
             for (int r = 0; r < kFT; ++r) {
               const float* src = w + (size_t)(tt * kFT + r) * H + c * kKC;
               for (int e = 0; e < kKC; ++e) {
@@ -931,15 +994,15 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
 
   // ---- device blob ----
   auto align_up = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
-  const int slots = f->slots_max;
+  const int slots = std::max(1, kCtasPerSm * f->num_sms / NT);  // upper bound; refined below from the occupancy
   const size_t off_big = 0;
   const size_t off_small = align_up(off_big + big_elems * 2);
   const size_t off_perm = align_up(off_small + small_floats * 4);
   const size_t off_consts = align_up(off_perm + perm.size() * 4);
   const size_t off_act = align_up(off_consts + consts.size() * 4);
-  const size_t act_bytes = (size_t)slots * 2 * NT * kChunkBytes;
+  const size_t act_bytes = (size_t)slots * 2 * NT * kAChunkStride;
   const size_t off_partial = align_up(off_act + act_bytes);
-  const size_t partial_bytes = (size_t)slots * 2 * NT * kRT * kPad * 4;
+  const size_t partial_bytes = (size_t)slots * 2 * NT * kRTMax * kPad * 4;
   const size_t off_flags = align_up(off_partial + partial_bytes);
   const size_t flag_bytes = ((size_t)slots * 2 * NT * 2 + 2) * 4;
   f->blob_bytes = align_up(off_flags + flag_bytes);
@@ -955,9 +1018,27 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   if (e == cudaSuccess) e = cudaMemcpy(base + off_small, small.data(), small_floats * 4, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(base + off_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(base + off_consts, consts.data(), consts.size() * 4, cudaMemcpyHostToDevice);
-  f->smem_bytes = sizeof(FlowSmem) + 1024;
+  f->smem32 = sizeof(FlowSmem<32>) + 1024;
+  f->smem64 = sizeof(FlowSmem<64>) + 1024;
+  f->smem_bytes = f->smem64;
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(flow_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem_bytes);
+    e = cudaFuncSetAttribute(flow_inverse_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem32);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(flow_inverse_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem64);
+  if (e == cudaSuccess) {
+    // the teams spin on each other's flags, so every CTA of a launch must be resident: size the slot count from
+    // what the device really fits (two CTAs per SM by design)
+    int occ32 = 0, occ64 = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, flow_inverse_kernel<32>, kThreads, f->smem32);
+    if (e == cudaSuccess)
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, flow_inverse_kernel<64>, kThreads, f->smem64);
+    const int occ = std::min(occ32, occ64);
+    if (e == cudaSuccess && occ < 1) {
+      ikf_flow_destroy(f);
+      return fail(IKF_EDEVICE, "ikf_flow_create: the flow kernel does not fit on an SM of device %d", device);
+    }
+    f->slots_max = std::max(1, std::min(occ, kCtasPerSm) * f->num_sms / NT);
+  }
   if (e != cudaSuccess) {
     ikf_flow_destroy(f);
     return fail(IKF_ECUDA, "ikf_flow_create: device setup failed: %s", cudaGetErrorString(e));
@@ -975,7 +1056,7 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   p.flt_b = p.m_inv + kPad * kPad;
   p.lo = p.flt_b + kPad;
   p.hi = p.lo + kPad;
-  p.act = (__nv_bfloat16*)(base + off_act);
+  p.act = base + off_act;
   p.partial = (float*)(base + off_partial);
   p.act_flag = (uint32_t*)(base + off_flags);
   p.part_flag = p.act_flag + (size_t)slots * 2 * NT;
@@ -1011,7 +1092,10 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   p.in = in; p.in_ld = in_ld; p.cond = cond; p.cond_ld = cond_ld; p.cond_rows = cond_rows; p.cond_cols = cond_cols;
   p.out = out; p.out_ld = out_ld; p.out_cols = out_cols; p.batch = batch;
   p.block_first = block_first; p.block_last = block_last; p.finalize = finalize; p.clamp_out = clamp;
-  p.n_rowgroups = (batch + kRT - 1) / kRT;
+  // Row groups of 32 while that still fits in one wave of teams (more CTAs in flight, and a partner CTA on every SM
+  // to compute while a team waits on an exchange), 64 beyond.
+  const int rt = ((batch + 31) / 32 <= flow->slots_max) ? 32 : 64;
+  p.n_rowgroups = (batch + rt - 1) / rt;
   p.slots = std::min(p.n_rowgroups, flow->slots_max);
   p.epoch = flow->epoch;
   p.trace = flow->trace;
@@ -1025,8 +1109,9 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   void* args[] = {(void*)&p};
   // cooperative launch = the driver guarantees that all CTAs of all teams are co-resident (the teams spin on each
   // other's flags)
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)flow_inverse_kernel, dim3(grid), dim3(kThreads), args,
-                                              flow->smem_bytes, (cudaStream_t)stream);
+  const void* fn = rt == 32 ? (const void*)flow_inverse_kernel<32> : (const void*)flow_inverse_kernel<64>;
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args,
+                                              rt == 32 ? flow->smem32 : flow->smem64, (cudaStream_t)stream);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return fail(IKF_ECUDA, "%s: launch failed: %s", name, cudaGetErrorString(e));
   return IKF_OK;

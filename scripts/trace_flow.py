@@ -34,10 +34,11 @@ t0 = int(sa[sa > 0].min())
 s = sa[0]
 names = ["W0 issue", "A first", "A last", "st:sync", "st:done", "st:flag", "c:start", "c:full0", "c:mma end", "c:v ready", "c:staged", "p:start", "p:flags", "p:coupled"]
 print("layer " + " ".join(f"{n:>10s}" for n in names))
-for i in range(nl):
+for i in range(8):
     row = [(int(v) - t0) / 1000.0 if v > 0 else float("nan") for v in s[i, :14]]
     print(f"{i:5d} " + " ".join(f"{v:10.2f}" for v in row))
 
 print("per-CTA stamps of selected events (us):")
 for layer, ev, nm in [(1, 7, "full0"), (1, 8, "mma end"), (1, 5, "flag"), (3, 11, "p:start"), (3, 12, "p:flags"), (4, 10, "L0 staged")]:
     print(f"layer {layer} {nm:>10s}: " + " ".join(f"{(int(v) - t0) / 1000.0:7.2f}" for v in sa[:, layer, ev]))
+
