@@ -103,6 +103,9 @@ def get_ik_solver(
         return ik_solver, hyper_parameters
 
     try:
+        cached = os.path.join(MODELS_DIR, model_filename(model_weights_url))
+        if synthetic_seed is not None and os.environ.get("IKFLOW_B200_OFFLINE") == "1" and not os.path.isfile(cached):
+            raise OSError("offline (IKFLOW_B200_OFFLINE=1) and the weight file is not cached")
         model_weights_filepath = download_model(model_weights_url)
     except (urllib.error.URLError, OSError) as e:
         if synthetic_seed is None:

@@ -1,0 +1,119 @@
+"""End-to-end: IKFlowSolver on the GPU against the oracle solver on identical latent draws, and the reference's own
+integration assertions (tests/ikflow_solver_test.py:56-117) as far as they apply without the released weights."""
+import pytest
+import torch
+
+import ikflow_b200
+from ikflow_b200 import _lib, ikflow_solver
+from ikflow_b200.model import IkflowModelParameters, make_synthetic_state_dict
+from oracle import jrl_kinematics as jk
+from oracle.solver import OracleSolver
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def panda_solver():
+    solver, hp = ikflow_b200.get_ik_solver("panda__full__lp191_5.25m", synthetic_seed=0)
+    sd = make_synthetic_state_dict(hp, solver.robot.actuated_joints_limits, seed=0)
+    oracle = OracleSolver(jk.PANDA, sd, hp.nb_nodes, hp.dim_latent_space, hp.coeff_fn_config, hp.rnvp_clamp)
+    return solver, oracle, hp
+
+
+def test_get_ik_solver_api(panda_solver):
+    solver, _, hp = panda_solver
+    assert isinstance(solver, ikflow_b200.IKFlowSolver) and isinstance(hp, IkflowModelParameters)
+    assert solver.robot.name == "panda" and solver.ndof == 7 and solver.network_width == 7 and solver.dim_cond == 8
+    y = torch.tensor([0.5, 0.5, 0.5, 1.0, 0.0, 0.0, 0.0], device=DEV)
+    sol = solver.generate_ik_solutions(y, 10)  # examples/example.py usage
+    assert sol.shape == (10, 7) and sol.is_cuda
+    out = solver.generate_ik_solutions(y, 10, return_detailed=True)
+    assert len(out) == 6 and out[1].shape == (10,) and out[3].dtype == torch.bool
+    assert solver.solve_n_poses(y.repeat(4, 1)).shape == (4, 7)
+    with pytest.raises(AssertionError, match="Cuda is available"):  # ikflow_solver.py:325-326
+        solver.generate_ik_solutions(y.cpu(), 10)
+
+
+def test_generate_ik_solutions_matches_oracle_on_identical_latents(panda_solver):
+    solver, oracle, _ = panda_solver
+    _, poses = jk.sample_joint_angles_and_poses(jk.PANDA, 512, seed=10)
+    for scale in (1.0, 0.75):  # 0.75 = scripts/evaluate.py:35
+        latent = scale * torch.randn(512, 7, generator=torch.Generator().manual_seed(11))
+        got = solver.generate_ik_solutions(poses.to(DEV), latent=latent.to(DEV)).cpu()
+        ref = oracle.generate_ik_solutions(poses, latent=latent)
+        assert (got - ref).abs().max() < 1e-4
+        assert torch.equal(got, jk.clamp_to_joint_limits(jk.PANDA, got.clone()))
+
+
+def test_latent_distribution_draws_are_torch_draws(panda_solver):
+    solver, _, _ = panda_solver
+    _, poses = jk.sample_joint_angles_and_poses(jk.PANDA, 33, seed=12)
+    torch.manual_seed(5)
+    a = solver.generate_ik_solutions(poses.to(DEV), latent_distribution="uniform", latent_scale=0.5)
+    torch.manual_seed(5)
+    latent = ikflow_b200.draw_latent("uniform", 0.5, (33, 7), DEV)
+    b = solver.generate_ik_solutions(poses.to(DEV), latent=latent)
+    assert torch.equal(a, b)
+
+
+def test_exact_solutions_match_oracle_solver_with_injected_latents(panda_solver, monkeypatch):
+    """config 3 semantics on untrained weights: identical latent stream into both implementations -> identical valid
+    masks (away from the thresholds) and matching solutions."""
+    solver, oracle, _ = panda_solver
+    n = 300
+    q_true, poses = jk.sample_joint_angles_and_poses(jk.PANDA, n, seed=13)
+    draws = []
+
+    def recording_latent(dist, scale, shape, device):
+        z = torch.randn(shape, generator=torch.Generator().manual_seed(100 + len(draws)))
+        draws.append(z)
+        return z.to(device)
+
+    monkeypatch.setattr(ikflow_solver, "draw_latent", recording_latent)
+    sol, valid = solver.generate_exact_ik_solutions(poses.to(DEV), repeat_counts=(1, 3), pos_error_threshold=1e-3, rot_error_threshold=1e-2)
+    it = iter(draws)
+    oracle.latent_source = lambda shape, dev: next(it)
+    ref_sol, ref_valid = oracle.generate_exact_ik_solutions(poses, repeat_counts=(1, 3), pos_error_threshold=1e-3, rot_error_threshold=1e-2, run_lma_on_cpu=False)
+    sol, valid = sol.cpu(), valid.cpu()
+    assert sol.shape == (n, 7) and valid.dtype == torch.bool
+    assert (valid == ref_valid).float().mean() > 0.98
+    both = valid & ref_valid
+    if both.any():
+        assert (sol[both] - ref_sol[both]).abs().max(dim=1).values.median() < 1e-4
+        pe, re = jk.pose_error(jk.PANDA, sol[valid], poses[valid])
+        assert (pe < 1e-3 + 2e-6).all() and (re < 1e-2 + 2e-5).all()
+
+
+def test_exact_solutions_converge_from_good_seeds(panda_solver, monkeypatch):
+    """The reference's closure assertions (tests/ikflow_solver_test.py:82-87) with flow seeds replaced by
+    truth + noise -- what a trained flow would deliver (cm-level seeds)."""
+    solver, _, _ = panda_solver
+    n = 1000
+    g = torch.Generator().manual_seed(3)
+    q_true = solver.robot.sample_joint_angles(n, generator=g)
+    poses = solver.robot.forward_kinematics(q_true)
+    real_inverse = solver.nn_model.inverse
+
+    def seeded_inverse(latent, cond, out_cols=None, clamp=False):
+        r = latent.shape[0] // cond.shape[0]
+        noise = 0.03 * torch.randn(latent.shape[0], 7, generator=torch.Generator().manual_seed(7)).to(latent.device)
+        # poses of later passes are subsets: recover their truth by matching pose rows
+        idx = (cond[:, None, :7] == poses[None, :, :]).all(-1).float().argmax(1)
+        return solver.robot.clamp_to_joint_limits((q_true[idx].repeat(r, 1) + noise).contiguous())
+
+    monkeypatch.setattr(solver.nn_model, "inverse", seeded_inverse)
+    launches0 = _lib.launch_count()
+    sol, valid = solver.generate_exact_ik_solutions(poses, pos_error_threshold=1e-3, rot_error_threshold=1e-2)
+    monkeypatch.setattr(solver.nn_model, "inverse", real_inverse)
+    assert valid.float().mean() > 0.97
+    pe, re = solver.robot.pose_errors(sol[valid], poses[valid])
+    assert pe.max() < 1e-3 and re.max() < 1e-2
+    assert torch.equal(sol, solver.robot.clamp_to_joint_limits(sol.clone()))
+    assert _lib.launch_count() - launches0 <= 12  # <= 3 passes x (clamp + refine) + checks: no per-row Python loop
+
+
+def test_smoke_entry_point():
+    import __graft_entry__
+
+    __graft_entry__.smoke()
