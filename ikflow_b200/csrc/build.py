@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB_DIR = os.path.join(os.path.dirname(HERE), "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libikflow_b200.so")
 SOURCES = ["api.cu", "robot.cu", "flow.cu"]
-HEADERS = ["common.h", os.path.join(ROOT, "include", "ikflow_b200.h")]
+HEADERS = ["common.h", "flow_common.cuh", "flow_mma.cuh", "flow_umma.cuh", os.path.join(ROOT, "include", "ikflow_b200.h")]
 
 
 def _nvcc() -> str:

@@ -1,0 +1,660 @@
+// Flow engine "umma": the hidden layers on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// Same algorithm and exchange protocol as flow_mma.cuh, different tiling:
+//   * CTA tile = 128 hidden features (UMMA M = 128, the WEIGHTS are the A operand: nn.Linear stores [out, in], i.e.
+//     K-major rows) x RT batch rows (UMMA N = RT, the ACTIVATIONS are the B operand, also K-major), D[128][RT] fp32 in
+//     TMEM: lane = feature, column = row;
+//   * team = hidden/128 CTAs (8 for the released models), one CTA per SM;
+//   * per 64-wide k-chunk: 4 k16 steps x 3 products (tail*head, head*tail, head*head) = 12 tcgen05.mma issued by one
+//     thread, operands straight from the swizzled ring stages (K-major SWIZZLE_128B descriptors), stage release and
+//     "accumulator ready" signalled by tcgen05.commit on mbarriers;
+//   * epilogue warps: tcgen05.ld (thread = feature), bias + LeakyReLU, head/tail split, publish; first and last layer
+//     of every subnet in fp32 FMA as before.
+// Requires hidden % 128 == 0 and hidden <= 1024.
+#pragma once
+
+#include "flow_common.cuh"
+
+namespace ikf {
+namespace umma {
+
+constexpr int kFTU = 128;                       // hidden features per CTA
+constexpr int kWPlaneU = kFTU * kKC * 2;        // one bf16 plane of a weight chunk [128][64]: 16 KB
+constexpr int kWChunkU = 2 * kWPlaneU;          // head + tail: 32 KB
+constexpr int kAStrideU = 2 * 2 * kRTMax * kKC * 2;  // scratch bytes reserved per producer: 2 k-chunks x (head+tail): 32 KB
+constexpr int kEpiWarps = 4;
+constexpr int kEpiThreads = kEpiWarps * 32;
+// One bulk copy keeps its issuing thread busy for ~0.3-0.45 us whatever its size; copies issued by different warps run
+// concurrently (scripts/ubench/ingest2.cu).  Four loader warps take the k-chunks round robin so that four copies are
+// always being issued.
+constexpr int kLoaderWarps = 4;
+constexpr int kLoaderWarpU = kEpiWarps;  // first loader warp
+constexpr int kMmaWarpU = kEpiWarps + kLoaderWarps;
+constexpr int kStorerWarpU = kMmaWarpU + 1;
+constexpr int kThreadsU = (kStorerWarpU + 1) * 32;
+// per (subnet, feature tile) small fp32 parameters:
+//   first_wT [16 k][128 f] | first_b [128] | big_b [kMaxBig][128] | last_w [16 o][128 f] (float4 slots XOR (o>>2)) | last_b [16]
+constexpr int kSmFirstW = 0;
+constexpr int kSmFirstB = kSmFirstW + kPad * kFTU;
+constexpr int kSmBigB = kSmFirstB + kFTU;
+constexpr int kSmLastW = kSmBigB + kMaxBig * kFTU;
+constexpr int kSmLastB = kSmLastW + kPad * kFTU;
+constexpr int kSmallFloatsU = kSmLastB + kPad;  // 4624
+constexpr int kSmallBytesU = kSmallFloatsU * 4;  // 18496
+static_assert(kSmallBytesU % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+template <int RT>
+struct Cfg {
+  static constexpr int kAPlane = RT * kKC * 2;       // one bf16 plane of an activation k-chunk [RT][64]
+  static constexpr int kAChunk = 2 * kAPlane;        // head + tail
+  static constexpr int kStage = kWChunkU + kAChunk;  // 40 KB (RT=32) / 48 KB (RT=64)
+  static constexpr int kStages = RT == 32 ? 4 : 2;
+  // loader warp w owns the ring stages s with s % kLoaders == w: its waits on a stage's barriers are then strictly in
+  // order (a waiter may lag an mbarrier by at most one phase)
+  static constexpr int kLoaders = kStages < kLoaderWarps ? kStages : kLoaderWarps;
+  static_assert(kStages % kLoaders == 0, "every stage needs exactly one owner");
+  static constexpr int kOutbox = 2 * kAChunk;        // the CTA's 128 features = two k-chunks; = RT*512 bytes
+  static constexpr int kTmemCols = RT <= 32 ? 32 : (RT <= 64 ? 64 : 128);
+  static constexpr int kOutPerThread = RT / 8;       // last-layer outputs per epilogue thread (RT*16 / 128)
+  static constexpr int kThreadsPerRow = 16 / kOutPerThread;
+  static_assert(kStage % 1024 == 0, "stages must keep the 1024-byte alignment of the swizzle atoms");
+};
+
+template <int RT>
+struct __align__(1024) Smem {
+  using C = Cfg<RT>;
+  uint8_t ring[C::kStages][C::kStage];  // [weights head|tail][activations head|tail]
+  // publish staging (two swizzled bf16 k-chunks)  |  fp32 activations [RT][128] for the last layer  |  landing zone of
+  // the team's partial tiles [NT][RT][16]
+  uint8_t outbox[C::kOutbox];
+  float ptile[RT * kPad];  // this CTA's partial sums of the last layer
+  float small[2][kSmallFloatsU];
+  float u[RT][kPad];    // flow state
+  float xin[RT][kPad];  // input of the current subnet: [state half | condition | 0]
+  float cnd[RT][8];
+  float a[RT][kPad];    // output of the last layer of the current subnet
+  uint64_t full[C::kStages], empty[C::kStages];
+  uint64_t small_full[2], small_empty[2];
+  uint64_t staging_free, dfull, dempty, pland_full;
+  uint32_t tmem_base;
+};
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 64 bf16 (128 B), 8-row swizzle atoms 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);  // start address >> 4
+  d |= (uint64_t)1 << 16;                  // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                  // descriptor version 1 (sm_100)
+  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M x N
+__device__ __host__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(
+          tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// All tensor-core work of one 64-wide k-chunk in a single asm block: the issuing thread is the bottleneck when N is
+// small (every instruction around an MMA costs ~5 cycles of a lone warp), so the descriptors are advanced with one
+// add each (k16 step = +32 bytes = +2 in the 16-byte address field) and the accumulate predicates are set up once.
+__device__ __forceinline__ void mma_chunk_x3(uint32_t tmem_d, uint32_t idesc, uint64_t wh, uint64_t wl, uint64_t ah,
+                                             uint64_t al, uint32_t acc_first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p0, p1;\n\t"
+      ".reg .b64 wh, wl, ah, al;\n\t"
+      "setp.ne.b32 p0, %6, 0;\n\t"
+      "setp.eq.b32 p1, %6, %6;\n\t"
+      "mov.b64 wh, %2;\n\tmov.b64 wl, %3;\n\tmov.b64 ah, %4;\n\tmov.b64 al, %5;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wl, ah, %1, p0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, al, %1, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, ah, %1, p1;\n\t"
+      "add.s64 wh, wh, 2;\n\tadd.s64 wl, wl, 2;\n\tadd.s64 ah, ah, 2;\n\tadd.s64 al, al, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wl, ah, %1, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, al, %1, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, ah, %1, p1;\n\t"
+      "add.s64 wh, wh, 2;\n\tadd.s64 wl, wl, 2;\n\tadd.s64 ah, ah, 2;\n\tadd.s64 al, al, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wl, ah, %1, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, al, %1, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, ah, %1, p1;\n\t"
+      "add.s64 wh, wh, 2;\n\tadd.s64 wl, wl, 2;\n\tadd.s64 ah, ah, 2;\n\tadd.s64 al, al, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wl, ah, %1, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, al, %1, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, ah, %1, p1;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(idesc), "l"(wh), "l"(wl), "l"(ah), "l"(al), "r"(acc_first)
+      : "memory");
+}
+__device__ __forceinline__ void mma_chunk_x1(uint32_t tmem_d, uint32_t idesc, uint64_t wh, uint64_t ah, uint32_t acc_first) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p0, p1;\n\t"
+      ".reg .b64 wh, ah;\n\t"
+      "setp.ne.b32 p0, %4, 0;\n\t"
+      "setp.eq.b32 p1, %4, %4;\n\t"
+      "mov.b64 wh, %2;\n\tmov.b64 ah, %3;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, ah, %1, p0;\n\t"
+      "add.s64 wh, wh, 2;\n\tadd.s64 ah, ah, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, ah, %1, p1;\n\t"
+      "add.s64 wh, wh, 2;\n\tadd.s64 ah, ah, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, ah, %1, p1;\n\t"
+      "add.s64 wh, wh, 2;\n\tadd.s64 ah, ah, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, ah, %1, p1;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(idesc), "l"(wh), "l"(ah), "r"(acc_first)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+__device__ __forceinline__ void bar_staged_arrive_u() {
+  asm volatile("bar.arrive 2, %0;" ::"n"(kEpiThreads + 32) : "memory");
+}
+__device__ __forceinline__ void bar_staged_sync_u() {
+  asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads + 32) : "memory");
+}
+__device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int RT>
+__global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const FlowParams p) {
+  using C = Cfg<RT>;
+  constexpr int kStages = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  Smem<RT>& sm = *reinterpret_cast<Smem<RT>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int NT = p.NT;            // hidden / 128
+  const int KCH = p.H / kKC;      // 64-wide k-chunks per hidden layer (2 per producer)
+  const int slot = blockIdx.x / NT;
+  const int t = blockIdx.x % NT;
+  const uint32_t launch_id = p.epoch;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&sm.small_full[b], 1);
+      mbar_init(&sm.small_empty[b], kEpiWarps);
+    }
+    mbar_init(&sm.staging_free, 1);
+    mbar_init(&sm.dfull, 1);
+    mbar_init(&sm.dempty, kEpiWarps);
+    mbar_init(&sm.pland_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == kMmaWarpU) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)),
+                 "n"(C::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  uint8_t* act_slot = p.act + (size_t)slot * 2 * NT * kAStrideU;
+  float* part_slot = p.partial + (size_t)slot * 2 * NT * kRTMax * kPad;
+  uint32_t* aflag = p.act_flag + (size_t)slot * 2 * NT;
+  uint32_t* pflag = p.part_flag + (size_t)slot * 2 * NT;
+
+  const int n_blocks = p.block_first - p.block_last + 1;
+  const int steps_per_rg = 2 * n_blocks;
+  const int my_rgs = (p.n_rowgroups - slot + p.slots - 1) / p.slots;
+  const int total_steps = my_rgs * steps_per_rg;
+
+  if (warp >= kLoaderWarpU && warp < kLoaderWarpU + kLoaderWarps) {
+    // ===== loaders: bulk-TMA producers.  k-chunk number pos = ring_pos + i (counted over the whole launch) goes to ring
+    // stage pos % kStages and is loaded by loader warp pos % kLoaders; warp 0 also prefetches the small parameters and
+    // pulls the next layer's weights into L2.  Chunks are consumed in the fixed order kc = (2t + i) % KCH, so the
+    // accumulation order never depends on timing.
+    const int lw = warp - kLoaderWarpU;
+    uint32_t ring_pos = 0;
+    uint32_t act_w[2] = {0, 0};
+    uint32_t xchg = 0;
+    auto prefetch_small = [&](int g) {
+      if (g >= total_steps) return;
+      const int b = g & 1;
+      if (g >= 2) mbar_wait(&sm.small_empty[b], ((g >> 1) - 1) & 1);
+      if (lane == 0) {
+        const int in_rg = g % steps_per_rg;
+        const int n = 2 * (p.block_first - in_rg / 2) + (in_rg & 1);
+        mbar_arrive_expect_tx(&sm.small_full[b], kSmallBytesU);
+        bulk_g2s(sm.small[b], p.small + ((size_t)n * NT + t) * kSmallFloatsU, kSmallBytesU, &sm.small_full[b]);
+      }
+      __syncwarp();
+    };
+    if (lw == 0) prefetch_small(0);
+    bool gave_up = false;
+    for (int g = 0; g < total_steps; ++g) {
+      const int in_rg = g % steps_per_rg;
+      const int n = 2 * (p.block_first - in_rg / 2) + (in_rg & 1);
+      for (int l = 0; l < p.n_big; ++l) {
+        const int buf = xchg & 1;
+        const uint32_t expected = p.epoch + 1 + act_w[buf];
+        const uint8_t* wbase =
+            reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n * p.n_big + l) * NT + t) * KCH * kWChunkU;
+        const uint8_t* abase = act_slot + (size_t)buf * NT * kAStrideU;
+        const uint32_t* my_flag = aflag + buf * NT + (lane < NT ? lane : 0);
+        if (lw == 0) {
+          // next hidden layer's weight slice (KCH x 32 KB) into L2, one layer ahead of its use
+          int n2 = n, l2 = l + 1;
+          if (l2 == p.n_big) {
+            l2 = 0;
+            n2 = -1;
+            if (g + 1 < total_steps) {
+              const int in_rg2 = (g + 1) % steps_per_rg;
+              n2 = 2 * (p.block_first - in_rg2 / 2) + (in_rg2 & 1);
+            }
+          }
+          if (n2 >= 0) {
+            const uint8_t* wnext =
+                reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n2 * p.n_big + l2) * NT + t) * KCH * kWChunkU;
+            for (int k = lane; k < KCH; k += 32) bulk_prefetch_l2(wnext + (size_t)k * kWChunkU, kWChunkU);
+          }
+        }
+        uint32_t ready = gave_up ? 0xffffffffu : 0u;  // bit c: producer c has published (warp-uniform)
+        for (int i = (lw + C::kLoaders - (int)(ring_pos % C::kLoaders)) % C::kLoaders; i < KCH; i += C::kLoaders) {
+          if (lw >= C::kLoaders) break;
+          const uint32_t pos = ring_pos + i;
+          const int st = pos % kStages;
+          const uint32_t use = pos / kStages;
+          if (g == 0 && l == 1 && lane == 0) trace_ev(p, 100 + i, 0);
+          if (use > 0) mbar_wait(&sm.empty[st], (use - 1) & 1);
+          if (g == 0 && l == 1 && lane == 0) trace_ev(p, 100 + i, 1);
+          const int kc = (2 * t + i) % KCH;
+          const int c = kc >> 1;
+          const void* wsrc = wbase + (size_t)kc * kWChunkU;
+          const void* asrc = abase + (size_t)c * kAStrideU + (size_t)(kc & 1) * C::kAChunk;
+          // one look at the flags: if the producer is already done, weights and activations go out together
+          if (!((ready >> c) & 1u)) {
+            bool ok = false;
+            if (lane < NT && !((ready >> lane) & 1u)) ok = (int32_t)(ld_relaxed(my_flag) - expected) >= 0;
+            ready |= __ballot_sync(0xffffffffu, ok);
+          }
+          const bool a_now = (ready >> c) & 1u;
+          if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], C::kStage);
+          __syncwarp();
+          if (lane == 0) bulk_g2s(sm.ring[st], wsrc, kWChunkU, &sm.full[st]);
+          if (lane == 1 && a_now) bulk_g2s(sm.ring[st] + kWChunkU, asrc, C::kAChunk, &sm.full[st]);
+          __syncwarp();
+          if (g == 0 && l == 1 && lane == 0) trace_ev(p, 100 + i, 2 + (a_now ? 0 : 8));
+          if (lane == 0 && i == 0) trace_ev(p, g * 4 + l, 0);
+          if (!a_now) {
+            uint32_t spins = 0;
+            long long t0 = 0;
+            while (!((ready >> c) & 1u)) {
+              bool ok = false;
+              if (lane < NT && !((ready >> lane) & 1u)) ok = (int32_t)(ld_relaxed(my_flag) - expected) >= 0;
+              ready |= __ballot_sync(0xffffffffu, ok);
+              if ((ready >> c) & 1u) break;
+              ++spins;
+              if (spins == 64) t0 = clock64();
+              if (spins > 64) {
+                __nanosleep(20);
+                if ((spins & 255u) == 0) {
+                  int bail = 0;
+                  if (lane == 0) {
+                    if (ld_relaxed(p.status + 1) == launch_id) bail = 1;
+                    else if (clock64() - t0 > 2500000000LL) {
+                      atomicOr(p.status, IKF_STATUS_SYNC_TIMEOUT);
+                      atomicExch(p.status + 1, launch_id);
+                      bail = 1;
+                    }
+                  }
+                  if (__shfl_sync(0xffffffffu, bail, 0)) {
+                    gave_up = true;
+                    ready = 0xffffffffu;
+                  }
+                }
+              }
+            }
+            if (lane == 0) bulk_g2s(sm.ring[st] + kWChunkU, asrc, C::kAChunk, &sm.full[st]);
+            __syncwarp();
+          }
+          if (lane == 0) {
+            if (i == 0) trace_ev(p, g * 4 + l, 1);
+            if (i == KCH - 1) trace_ev(p, g * 4 + l, 2);
+          }
+        }
+        if (lw == 0 && l == 0) prefetch_small(g + 1);
+        ring_pos += KCH;
+        ++act_w[buf];
+        ++xchg;
+      }
+      if (lw == 0 && p.n_big == 0) prefetch_small(g + 1);
+    }
+  } else if (warp == kMmaWarpU) {
+    // ===== MMA issuer: one thread drives the tensor core =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kFTU, RT);
+      uint32_t ring_pos = 0;
+      uint32_t layers = 0;  // hidden layers issued so far
+      const bool x3 = p.precision == IKF_PRECISION_BF16X3;
+      for (int g = 0; g < total_steps; ++g) {
+        for (int l = 0; l < p.n_big; ++l) {
+          if (layers > 0) mbar_wait(&sm.dempty, (layers - 1) & 1);  // the epilogue has drained the accumulator
+          tc_fence_after();
+          for (int i = 0; i < KCH; ++i) {
+            const int s = ring_pos % kStages;
+            if (g == 0 && l == 1) trace_ev(p, 100 + i, 3);
+            mbar_wait(&sm.full[s], (ring_pos / kStages) & 1);
+            if (g == 0 && l == 1) trace_ev(p, 100 + i, 4);
+            tc_fence_after();
+            const uint32_t w_hi = smem_u32(sm.ring[s]);
+            const uint32_t w_lo = w_hi + kWPlaneU;
+            const uint32_t a_hi = w_hi + kWChunkU;
+            const uint32_t a_lo = a_hi + C::kAPlane;
+            if (x3)
+              mma_chunk_x3(tmem, idesc, make_desc(w_hi), make_desc(w_lo), make_desc(a_hi), make_desc(a_lo), i != 0);
+            else
+              mma_chunk_x1(tmem, idesc, make_desc(w_hi), make_desc(a_hi), i != 0);
+            mma_commit(&sm.empty[s]);  // the stage is free once these MMAs have read it
+            if (g == 0 && l == 1) trace_ev(p, 100 + i, 5);
+            ++ring_pos;
+          }
+          mma_commit(&sm.dfull);  // accumulator complete
+          trace_ev(p, g * 4 + l, 8);
+          ++layers;
+        }
+      }
+    }
+  } else if (warp == kStorerWarpU) {
+    // ===== storer: publishes this CTA's 128 features (two k-chunks) to the team =====
+    uint32_t act_w[2] = {0, 0};
+    uint32_t xchg = 0;
+    for (int g = 0; g < total_steps; ++g) {
+      for (int l = 0; l < p.n_big; ++l) {
+        const int buf = xchg & 1;
+        bar_staged_sync_u();
+        if (lane == 0) {
+          uint8_t* dst = act_slot + ((size_t)buf * NT + t) * kAStrideU;
+          trace_ev(p, g * 4 + l, 3);
+          bulk_s2g(dst, sm.outbox, C::kOutbox);
+          bulk_commit();
+          bulk_wait_all();
+          trace_ev(p, g * 4 + l, 4);
+          // wait_group returned: the bulk store is complete, its bytes are in L2 (the point of coherence) before the
+          // flag store below even leaves this thread, and consumers read both through L2 -- so a relaxed store is
+          // enough; st.release would add a ~1 us MEMBAR.GPU to every exchange
+          st_relaxed(aflag + buf * NT + t, p.epoch + 1 + act_w[buf]);
+          trace_ev(p, g * 4 + l, 5);
+          mbar_arrive(&sm.staging_free);
+        }
+        __syncwarp();
+        ++act_w[buf];
+        ++xchg;
+      }
+    }
+  } else {
+    // ===== epilogue / SIMT warps: thread f owns hidden feature 128 t + f (TMEM lane f) =====
+    const int f = tid;
+    const int sub = f >> 6;  // which of the CTA's two 64-wide k-chunks
+    const int kf = f & 63;
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t part_w[2] = {0, 0};
+    uint32_t pxchg = 0;
+    uint32_t staged = 0;
+    uint32_t layers = 0;  // hidden layers drained so far
+    constexpr int OPT = C::kOutPerThread, TPR = C::kThreadsPerRow;
+    const int prow = tid / TPR, pog = tid % TPR;  // last layer: row and first output (pog * OPT) of this thread
+
+    int g = 0;
+    for (int rg = slot; rg < p.n_rowgroups; rg += p.slots) {
+      for (int i = tid; i < RT * kPad; i += kEpiThreads) {
+        const int r = i / kPad, j = i % kPad;
+        const int row = rg * RT + r;
+        float uv = 0.f, cv = 0.f;
+        if (row < p.batch) {
+          if (j < p.W) uv = p.in[(size_t)row * p.in_ld + j];
+          if (j < p.cond_cols) cv = p.cond[(size_t)(row % p.cond_rows) * p.cond_ld + j];
+        }
+        sm.u[r][j] = uv;
+        if (j < 8) sm.cnd[r][j] = cv;
+      }
+      bar_epi();
+
+      for (int blk = p.block_first; blk >= p.block_last; --blk) {
+        for (int sidx = 0; sidx < 2; ++sidx, ++g) {
+          const int sb = g & 1;
+          const float* sp = sm.small[sb];
+          const int in_off = sidx == 0 ? 0 : p.s1;
+          const int in_len = sidx == 0 ? p.s1 : p.s2;
+          const int tg_off = sidx == 0 ? p.s1 : 0;
+          const int tg_len = sidx == 0 ? p.s2 : p.s1;
+          const int kin = in_len + p.dim_cond;
+          // subnet input [state half | condition]
+          for (int i = tid; i < RT * kPad; i += kEpiThreads) {
+            const int r = i / kPad, k = i % kPad;
+            sm.xin[r][k] = k < in_len ? sm.u[r][in_off + k] : (k < kin ? sm.cnd[r][k - in_len] : 0.f);
+          }
+          mbar_wait(&sm.small_full[sb], (g >> 1) & 1);
+          bar_epi();
+
+          float v[RT];  // activations of feature f for the RT rows
+          // ---- first layer: fp32 FMA ----
+          {
+            const float b0 = sp[kSmFirstB + f];
+#pragma unroll
+            for (int r = 0; r < RT; ++r) v[r] = b0;
+            for (int k4 = 0; k4 < kin; k4 += 4) {  // xin is zero-padded to 16 columns, the weights too
+              const float w0 = sp[kSmFirstW + (k4 + 0) * kFTU + f], w1 = sp[kSmFirstW + (k4 + 1) * kFTU + f];
+              const float w2 = sp[kSmFirstW + (k4 + 2) * kFTU + f], w3 = sp[kSmFirstW + (k4 + 3) * kFTU + f];
+#pragma unroll
+              for (int r = 0; r < RT; ++r) {
+                const float4 x = *reinterpret_cast<const float4*>(&sm.xin[r][k4]);
+                v[r] = fmaf(x.x, w0, v[r]);
+                v[r] = fmaf(x.y, w1, v[r]);
+                v[r] = fmaf(x.z, w2, v[r]);
+                v[r] = fmaf(x.w, w3, v[r]);
+              }
+            }
+#pragma unroll
+            for (int r = 0; r < RT; ++r) v[r] = leaky(v[r]);
+          }
+
+          for (int l = 0; l <= p.n_big; ++l) {
+            if (l > 0) {
+              // ---- hidden layer l-1: drain the accumulator ----
+              if (tid == 0) trace_ev(p, g * 4 + l - 1, 6);
+              mbar_wait(&sm.dfull, layers & 1);
+              tc_fence_after();
+              if (tid == 0) trace_ev(p, g * 4 + l - 1, 7);
+#pragma unroll
+              for (int c0 = 0; c0 < RT; c0 += 32) {
+                float tmp[32];
+                tmem_ld32(taddr + c0, tmp);
+#pragma unroll
+                for (int r = 0; r < 32; ++r) v[c0 + r] = tmp[r];
+              }
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&sm.dempty);
+              ++layers;
+              const float bb = sp[kSmBigB + (l - 1) * kFTU + f];
+#pragma unroll
+              for (int r = 0; r < RT; ++r) v[r] = leaky(v[r] + bb);
+              if (tid == 0) trace_ev(p, g * 4 + l - 1, 9);
+            }
+            if (l < p.n_big) {
+              // ---- publish: head/tail split into the two swizzled k-chunks of the outbox ----
+              if (staged > 0) mbar_wait(&sm.staging_free, (staged - 1) & 1);
+              uint8_t* ob = sm.outbox + sub * C::kAChunk;
+#pragma unroll
+              for (int r = 0; r < RT; ++r) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(v[r]);
+                const __nv_bfloat16 lo = __float2bfloat16_rn(v[r] - __bfloat162float(h));
+                const uint32_t off = tile_off_bytes(r, kf);
+                *reinterpret_cast<__nv_bfloat16*>(ob + off) = h;
+                *reinterpret_cast<__nv_bfloat16*>(ob + C::kAPlane + off) = lo;
+              }
+              fence_proxy_async();
+              bar_staged_arrive_u();
+              if (tid == 0) trace_ev(p, g * 4 + l, 10);
+              ++staged;
+            }
+          }
+
+          // ---- last layer: fp32, through a transposed copy of the activations ----
+          if (tid == 0) trace_ev(p, g * 4 + 3, 11);
+          const int pb = pxchg & 1;
+          if (staged > 0) mbar_wait(&sm.staging_free, (staged - 1) & 1);
+          float* vt = reinterpret_cast<float*>(sm.outbox);  // [RT][128], float4 slots XOR-swizzled by row % 8
+#pragma unroll
+          for (int r = 0; r < RT; ++r) vt[r * kFTU + ((((f >> 2) ^ (r & 7)) << 2) | (f & 3))] = v[r];
+          bar_epi();
+          {
+            float po[OPT];
+#pragma unroll
+            for (int oo = 0; oo < OPT; ++oo) po[oo] = 0.f;
+            const float* vrow = vt + prow * kFTU;
+#pragma unroll 4
+            for (int j4 = 0; j4 < kFTU / 4; ++j4) {
+              const float4 x = *reinterpret_cast<const float4*>(vrow + ((j4 ^ (prow & 7)) << 2));
+#pragma unroll
+              for (int oo = 0; oo < OPT; ++oo) {
+                const int o = pog * OPT + oo;
+                const float4 w = *reinterpret_cast<const float4*>(sp + kSmLastW + o * kFTU + ((j4 ^ ((o >> 2) & 7)) << 2));
+                po[oo] = fmaf(x.x, w.x, po[oo]);
+                po[oo] = fmaf(x.y, w.y, po[oo]);
+                po[oo] = fmaf(x.z, w.z, po[oo]);
+                po[oo] = fmaf(x.w, w.w, po[oo]);
+              }
+            }
+#pragma unroll
+            for (int oo = 0; oo < OPT; ++oo) sm.ptile[prow * kPad + pog * OPT + oo] = po[oo];
+          }
+          fence_proxy_async();
+          bar_epi();
+          if (tid == 0) trace_ev(p, g * 4 + 3, 14);
+          const uint32_t pexp = p.epoch + 1 + part_w[pb];
+          if (warp == 0) {
+            if (lane == 0) {
+              bulk_s2g(part_slot + ((size_t)pb * NT + t) * RT * kPad, sm.ptile, RT * kPad * 4);
+              bulk_commit();
+              bulk_wait_all();
+              st_relaxed(pflag + pb * NT + t, pexp);  // see the storer
+              trace_ev(p, g * 4 + 3, 15);
+            }
+            __syncwarp();
+            for (int c = lane; c < NT; c += 32) wait_flag(pflag + pb * NT + c, pexp, p.status, launch_id);
+            __syncwarp();
+            fence_proxy_async();
+            if (lane == 0) {
+              // all partial tiles of the team in one copy: [NT][RT][16] fp32, over the (now dead) transposed tile
+              mbar_arrive_expect_tx(&sm.pland_full, NT * RT * kPad * 4);
+              bulk_g2s(sm.outbox, part_slot + (size_t)pb * NT * RT * kPad, NT * RT * kPad * 4, &sm.pland_full);
+            }
+          }
+          mbar_wait(&sm.pland_full, pxchg & 1);
+          if (tid == 0) trace_ev(p, g * 4 + 3, 12);
+          {
+            const float* land = reinterpret_cast<const float*>(sm.outbox);
+            for (int i = tid; i < RT * 4; i += kEpiThreads) {
+              const int r = i >> 2, o4 = i & 3;
+              float4 s = *reinterpret_cast<const float4*>(sp + kSmLastB + 4 * o4);
+              for (int c = 0; c < NT; ++c) {  // fixed order: bitwise identical replicas
+                const float4 x = *reinterpret_cast<const float4*>(land + ((size_t)c * RT + r) * kPad + 4 * o4);
+                s.x += x.x;
+                s.y += x.y;
+                s.z += x.z;
+                s.w += x.w;
+              }
+              *reinterpret_cast<float4*>(&sm.a[r][4 * o4]) = s;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.small_empty[sb]);
+          ++part_w[pb];
+          ++pxchg;
+          bar_epi();
+          for (int i = tid; i < RT * tg_len; i += kEpiThreads) {
+            const int r = i / tg_len, j = i % tg_len;
+            const float sc = p.clamp_scale * atanf(sm.a[r][j]);
+            const float tr = sm.a[r][tg_len + j];
+            sm.u[r][tg_off + j] = (sm.u[r][tg_off + j] - tr) * expf(-sc);
+          }
+          bar_epi();
+          if (tid == 0) trace_ev(p, g * 4 + 3, 13);
+        }
+        {
+          constexpr int kPer = (RT * kPad + kEpiThreads - 1) / kEpiThreads;
+          float tmp[kPer];
+#pragma unroll
+          for (int c = 0; c < kPer; ++c) {
+            const int i = tid + c * kEpiThreads;
+            tmp[c] = i < RT * p.W ? sm.u[i / p.W][p.perm_inv[blk * kPad + i % p.W]] : 0.f;
+          }
+          bar_epi();
+#pragma unroll
+          for (int c = 0; c < kPer; ++c) {
+            const int i = tid + c * kEpiThreads;
+            if (i < RT * p.W) sm.u[i / p.W][i % p.W] = tmp[c];
+          }
+          bar_epi();
+        }
+      }
+
+      if (t == 0) {
+        for (int i = tid; i < RT * p.out_cols; i += kEpiThreads) {
+          const int r = i / p.out_cols, j = i % p.out_cols;
+          const int row = rg * RT + r;
+          if (row >= p.batch) continue;
+          float o;
+          if (p.finalize) {
+            o = 0.f;
+            for (int k = 0; k < p.W; ++k) o = fmaf(sm.u[r][k] - p.flt_b[k], p.m_inv[k * kPad + j], o);
+            if (p.clamp_out && j < p.ndof) o = fminf(fmaxf(o, p.lo[j]), p.hi[j]);
+          } else {
+            o = sm.u[r][j];
+          }
+          if (!isfinite(o)) atomicOr(p.status, IKF_STATUS_NONFINITE);
+          p.out[(size_t)row * p.out_ld + j] = o;
+        }
+      }
+      bar_epi();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarpU) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(C::kTmemCols) : "memory");
+  }
+}
+
+}  // namespace umma
+}  // namespace ikf
