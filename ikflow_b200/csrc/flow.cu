@@ -229,7 +229,10 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
         float* blk = small.data() + ((size_t)n * NT + tt) * small_block;
         for (int o = 0; o < out_dim; ++o) {
           for (int e = 0; e < FT; ++e) {
-            const int pos = engine ? ((((e >> 2) ^ ((o >> 2) & 7)) << 2) | (e & 3)) : e;
+            // umma engine: float4 slot j4 = e / 4 of output row o is stored at slot (j4 & ~7) | ((j4 ^ (j4 >> 3) ^ (o >> 2)) & 7)
+            // so that the four k-quarters and the output groups read by one warp fall into different banks
+            const int j4 = e >> 2;
+            const int pos = engine ? ((((j4 & ~7) | ((j4 ^ (j4 >> 3) ^ (o >> 2)) & 7)) << 2) | (e & 3)) : e;
             blk[o_last_w + o * FT + pos] = wl[(size_t)o * H + tt * FT + e];
           }
           blk[o_last_b + o] = bl[o];

@@ -106,6 +106,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
+// The same for waits that are expected to be long (producer warps waiting for a free stage): sleep between probes so
+// that the spinning warp does not take issue slots from the warps that do the arithmetic on the same scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
 
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -124,6 +134,9 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy writes to shared memory -> async-proxy (bulk store) reads of it; the narrow form does not have to
+// order the global-memory traffic of the bulk copies that are in flight
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -185,6 +198,29 @@ __device__ __forceinline__ void trace_ev(const FlowParams& p, int layer, int ev)
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
     p.trace[((size_t)blockIdx.x * p.trace_layers + layer) * 16 + ev] = tns;
   }
+}
+
+// Explicit shared-space accesses.  The kernels reach their shared memory through a struct reference built from the
+// aligned dynamic-smem base, and nvcc then emits GENERIC loads/stores (LD.E / ST.E) for it -- measured 5x slower than
+// LDS/STS in the last-layer loop.  These wrappers take 32-bit shared addresses (smem_u32).
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint16_t v) {
+  asm volatile("st.shared.u16 [%1], %0;" ::"h"(v), "r"(a) : "memory");
 }
 
 __device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : v * kLeakySlope; }

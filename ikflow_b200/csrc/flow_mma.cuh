@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) flow_inverse_kernel(cons
                     *reinterpret_cast<uint32_t*>(sm.staging + off) = pack_bf16(h0, h1);
                     *reinterpret_cast<uint32_t*>(sm.staging + C::kATileBytes + off) = pack_bf16(l0, l1);
                   }
-              fence_proxy_async();
+              fence_proxy_async_smem();
               bar_staged_arrive();
               if (tid == 0) trace_ev(p, g * 4 + l, 10);
               ++staged;

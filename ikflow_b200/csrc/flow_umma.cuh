@@ -33,7 +33,8 @@ constexpr int kMmaWarpU = kEpiWarps + kLoaderWarps;
 constexpr int kStorerWarpU = kMmaWarpU + 1;
 constexpr int kThreadsU = (kStorerWarpU + 1) * 32;
 // per (subnet, feature tile) small fp32 parameters:
-//   first_wT [16 k][128 f] | first_b [128] | big_b [kMaxBig][128] | last_w [16 o][128 f] (float4 slots XOR (o>>2)) | last_b [16]
+//   first_wT [16 k][128 f] | first_b [128] | big_b [kMaxBig][128] | last_w [16 o][128 f] (float4 slots swizzled, see
+//   flow.cu) | last_b [16]
 constexpr int kSmFirstW = 0;
 constexpr int kSmFirstB = kSmFirstW + kPad * kFTU;
 constexpr int kSmBigB = kSmFirstB + kFTU;
@@ -54,7 +55,7 @@ struct Cfg {
   static constexpr int kLoaders = kStages < kLoaderWarps ? kStages : kLoaderWarps;
   static_assert(kStages % kLoaders == 0, "every stage needs exactly one owner");
   static constexpr int kOutbox = 2 * kAChunk;        // the CTA's 128 features = two k-chunks; = RT*512 bytes
-  static constexpr int kTmemCols = RT <= 32 ? 32 : (RT <= 64 ? 64 : 128);
+  static constexpr int kTmemCols = 2 * RT <= 32 ? 32 : (2 * RT <= 64 ? 64 : (2 * RT <= 128 ? 128 : 256));  // D[:, 0:2RT]
   static constexpr int kOutPerThread = RT / 8;       // last-layer outputs per epilogue thread (RT*16 / 128)
   static constexpr int kThreadsPerRow = 16 / kOutPerThread;
   static_assert(kStage % 1024 == 0, "stages must keep the 1024-byte alignment of the swizzle atoms");
@@ -100,35 +101,35 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t d
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// All tensor-core work of one 64-wide k-chunk in a single asm block: the issuing thread is the bottleneck when N is
-// small (every instruction around an MMA costs ~5 cycles of a lone warp), so the descriptors are advanced with one
-// add each (k16 step = +32 bytes = +2 in the 16-byte address field) and the accumulate predicates are set up once.
-__device__ __forceinline__ void mma_chunk_x3(uint32_t tmem_d, uint32_t idesc, uint64_t wh, uint64_t wl, uint64_t ah,
-                                             uint64_t al, uint32_t acc_first) {
+// All tensor-core work of one 64-wide k-chunk in a single asm block.  A tcgen05.mma costs the same ~65-80 cycles for
+// every N <= 128 (scripts/ubench/umma_rate.cu), so the three split-operand products are folded into TWO instructions
+// per k16 step by stacking the activation head and tail along N (they are adjacent in the stage: rows 0..RT-1 head,
+// RT..2RT-1 tail):   D[:, 0:2RT] += W_head * [A_head; A_tail]     (N = 2 RT)
+//                    D[:, 0:RT]  += W_tail * A_head               (N = RT)
+// and the epilogue adds the two halves of D.  Descriptors advance by one add per k16 step (+32 bytes = +2 in the
+// 16-byte address field); the accumulate predicates are set up once.
+__device__ __forceinline__ void mma_chunk_x3(uint32_t tmem_d, uint32_t idesc_2n, uint32_t idesc_n, uint64_t wh,
+                                             uint64_t wl, uint64_t a, uint32_t acc_first) {
   asm volatile(
       "{\n\t"
       ".reg .pred p0, p1;\n\t"
-      ".reg .b64 wh, wl, ah, al;\n\t"
+      ".reg .b64 wh, wl, a;\n\t"
       "setp.ne.b32 p0, %6, 0;\n\t"
       "setp.eq.b32 p1, %6, %6;\n\t"
-      "mov.b64 wh, %2;\n\tmov.b64 wl, %3;\n\tmov.b64 ah, %4;\n\tmov.b64 al, %5;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wl, ah, %1, p0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, al, %1, p1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, ah, %1, p1;\n\t"
-      "add.s64 wh, wh, 2;\n\tadd.s64 wl, wl, 2;\n\tadd.s64 ah, ah, 2;\n\tadd.s64 al, al, 2;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wl, ah, %1, p1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, al, %1, p1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, ah, %1, p1;\n\t"
-      "add.s64 wh, wh, 2;\n\tadd.s64 wl, wl, 2;\n\tadd.s64 ah, ah, 2;\n\tadd.s64 al, al, 2;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wl, ah, %1, p1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, al, %1, p1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, ah, %1, p1;\n\t"
-      "add.s64 wh, wh, 2;\n\tadd.s64 wl, wl, 2;\n\tadd.s64 ah, ah, 2;\n\tadd.s64 al, al, 2;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wl, ah, %1, p1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, al, %1, p1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, ah, %1, p1;\n\t"
+      "mov.b64 wh, %3;\n\tmov.b64 wl, %4;\n\tmov.b64 a, %5;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, a, %1, p0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wl, a, %2, p1;\n\t"
+      "add.s64 wh, wh, 2;\n\tadd.s64 wl, wl, 2;\n\tadd.s64 a, a, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, a, %1, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wl, a, %2, p1;\n\t"
+      "add.s64 wh, wh, 2;\n\tadd.s64 wl, wl, 2;\n\tadd.s64 a, a, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, a, %1, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wl, a, %2, p1;\n\t"
+      "add.s64 wh, wh, 2;\n\tadd.s64 wl, wl, 2;\n\tadd.s64 a, a, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, a, %1, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wl, a, %2, p1;\n\t"
       "}\n" ::"r"(tmem_d),
-      "r"(idesc), "l"(wh), "l"(wl), "l"(ah), "l"(al), "r"(acc_first)
+      "r"(idesc_2n), "r"(idesc_n), "l"(wh), "l"(wl), "l"(a), "r"(acc_first)
       : "memory");
 }
 __device__ __forceinline__ void mma_chunk_x1(uint32_t tmem_d, uint32_t idesc, uint64_t wh, uint64_t ah, uint32_t acc_first) {
@@ -178,9 +179,6 @@ __device__ __forceinline__ void bar_staged_arrive_u() {
 }
 __device__ __forceinline__ void bar_staged_sync_u() {
   asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads + 32) : "memory");
-}
-__device__ __forceinline__ void st_relaxed(uint32_t* p, uint32_t v) {
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 template <int RT>
@@ -248,7 +246,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
     auto prefetch_small = [&](int g) {
       if (g >= total_steps) return;
       const int b = g & 1;
-      if (g >= 2) mbar_wait(&sm.small_empty[b], ((g >> 1) - 1) & 1);
+      if (g >= 2) mbar_wait_relaxed(&sm.small_empty[b], ((g >> 1) - 1) & 1);
       if (lane == 0) {
         const int in_rg = g % steps_per_rg;
         const int n = 2 * (p.block_first - in_rg / 2) + (in_rg & 1);
@@ -292,9 +290,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
           const uint32_t pos = ring_pos + i;
           const int st = pos % kStages;
           const uint32_t use = pos / kStages;
-          if (g == 0 && l == 1 && lane == 0) trace_ev(p, 100 + i, 0);
-          if (use > 0) mbar_wait(&sm.empty[st], (use - 1) & 1);
-          if (g == 0 && l == 1 && lane == 0) trace_ev(p, 100 + i, 1);
+          if (use > 0) mbar_wait_relaxed(&sm.empty[st], (use - 1) & 1);
           const int kc = (2 * t + i) % KCH;
           const int c = kc >> 1;
           const void* wsrc = wbase + (size_t)kc * kWChunkU;
@@ -311,7 +307,6 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
           if (lane == 0) bulk_g2s(sm.ring[st], wsrc, kWChunkU, &sm.full[st]);
           if (lane == 1 && a_now) bulk_g2s(sm.ring[st] + kWChunkU, asrc, C::kAChunk, &sm.full[st]);
           __syncwarp();
-          if (g == 0 && l == 1 && lane == 0) trace_ev(p, 100 + i, 2 + (a_now ? 0 : 8));
           if (lane == 0 && i == 0) trace_ev(p, g * 4 + l, 0);
           if (!a_now) {
             uint32_t spins = 0;
@@ -360,30 +355,27 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
   } else if (warp == kMmaWarpU) {
     // ===== MMA issuer: one thread drives the tensor core =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kFTU, RT);
+      constexpr uint32_t idesc = make_idesc(kFTU, RT);       // N = RT
+      constexpr uint32_t idesc2 = make_idesc(kFTU, 2 * RT);  // N = 2 RT: activation head and tail stacked
       uint32_t ring_pos = 0;
       uint32_t layers = 0;  // hidden layers issued so far
       const bool x3 = p.precision == IKF_PRECISION_BF16X3;
+      const uint64_t d_wh0 = make_desc(smem_u32(sm.ring[0])), d_wl0 = make_desc(smem_u32(sm.ring[0]) + kWPlaneU);
+      const uint64_t d_a0 = make_desc(smem_u32(sm.ring[0]) + kWChunkU);
       for (int g = 0; g < total_steps; ++g) {
         for (int l = 0; l < p.n_big; ++l) {
           if (layers > 0) mbar_wait(&sm.dempty, (layers - 1) & 1);  // the epilogue has drained the accumulator
           tc_fence_after();
           for (int i = 0; i < KCH; ++i) {
             const int s = ring_pos % kStages;
-            if (g == 0 && l == 1) trace_ev(p, 100 + i, 3);
             mbar_wait(&sm.full[s], (ring_pos / kStages) & 1);
-            if (g == 0 && l == 1) trace_ev(p, 100 + i, 4);
             tc_fence_after();
-            const uint32_t w_hi = smem_u32(sm.ring[s]);
-            const uint32_t w_lo = w_hi + kWPlaneU;
-            const uint32_t a_hi = w_hi + kWChunkU;
-            const uint32_t a_lo = a_hi + C::kAPlane;
+            const uint64_t soff = (uint64_t)(s * (C::kStage >> 4));  // stage offset in the 16-byte address field
             if (x3)
-              mma_chunk_x3(tmem, idesc, make_desc(w_hi), make_desc(w_lo), make_desc(a_hi), make_desc(a_lo), i != 0);
+              mma_chunk_x3(tmem, idesc2, idesc, d_wh0 + soff, d_wl0 + soff, d_a0 + soff, i != 0);
             else
-              mma_chunk_x1(tmem, idesc, make_desc(w_hi), make_desc(a_hi), i != 0);
+              mma_chunk_x1(tmem, idesc, d_wh0 + soff, d_a0 + soff, i != 0);
             mma_commit(&sm.empty[s]);  // the stage is free once these MMAs have read it
-            if (g == 0 && l == 1) trace_ev(p, 100 + i, 5);
             ++ring_pos;
           }
           mma_commit(&sm.dfull);  // accumulator complete
@@ -407,10 +399,10 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
           bulk_commit();
           bulk_wait_all();
           trace_ev(p, g * 4 + l, 4);
-          // wait_group returned: the bulk store is complete, its bytes are in L2 (the point of coherence) before the
-          // flag store below even leaves this thread, and consumers read both through L2 -- so a relaxed store is
-          // enough; st.release would add a ~1 us MEMBAR.GPU to every exchange
-          st_relaxed(aflag + buf * NT + t, p.epoch + 1 + act_w[buf]);
+          // The release is NOT optional: completion of the bulk store (wait_group) makes its bytes visible to this
+          // thread only.  A relaxed flag store here lets consumers read stale chunks (scripts/stress_flow.py: 37 of
+          // 1500 calls differ); the MEMBAR.GPU of st.release costs ~1 us per exchange.
+          st_release(aflag + buf * NT + t, p.epoch + 1 + act_w[buf]);
           trace_ev(p, g * 4 + l, 5);
           mbar_arrive(&sm.staging_free);
         }
@@ -429,8 +421,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
     uint32_t pxchg = 0;
     uint32_t staged = 0;
     uint32_t layers = 0;  // hidden layers drained so far
-    constexpr int OPT = C::kOutPerThread, TPR = C::kThreadsPerRow;
-    const int prow = tid / TPR, pog = tid % TPR;  // last layer: row and first output (pog * OPT) of this thread
+    const bool x3 = p.precision == IKF_PRECISION_BF16X3;
 
     int g = 0;
     for (int rg = slot; rg < p.n_rowgroups; rg += p.slots) {
@@ -451,6 +442,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
         for (int sidx = 0; sidx < 2; ++sidx, ++g) {
           const int sb = g & 1;
           const float* sp = sm.small[sb];
+          const uint32_t sp_a = smem_u32(sm.small[sb]);  // explicit shared-space accesses (see lds128)
           const int in_off = sidx == 0 ? 0 : p.s1;
           const int in_len = sidx == 0 ? p.s1 : p.s2;
           const int tg_off = sidx == 0 ? p.s1 : 0;
@@ -467,19 +459,27 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
           float v[RT];  // activations of feature f for the RT rows
           // ---- first layer: fp32 FMA ----
           {
-            const float b0 = sp[kSmFirstB + f];
+            const float b0 = lds32(sp_a + (kSmFirstB + f) * 4);
 #pragma unroll
             for (int r = 0; r < RT; ++r) v[r] = b0;
+            const uint32_t xin_a = smem_u32(&sm.xin[0][0]);
             for (int k4 = 0; k4 < kin; k4 += 4) {  // xin is zero-padded to 16 columns, the weights too
-              const float w0 = sp[kSmFirstW + (k4 + 0) * kFTU + f], w1 = sp[kSmFirstW + (k4 + 1) * kFTU + f];
-              const float w2 = sp[kSmFirstW + (k4 + 2) * kFTU + f], w3 = sp[kSmFirstW + (k4 + 3) * kFTU + f];
+              const uint32_t wa = sp_a + (kSmFirstW + k4 * kFTU + f) * 4;
+              const float w0 = lds32(wa), w1 = lds32(wa + kFTU * 4), w2 = lds32(wa + 2 * kFTU * 4), w3 = lds32(wa + 3 * kFTU * 4);
+              // only four warps run this and every one is alone on its scheduler: issue the loads of 8 rows back to
+              // back, then the 32 FMAs that consume them, so that the shared-memory latency is paid once per batch
 #pragma unroll
-              for (int r = 0; r < RT; ++r) {
-                const float4 x = *reinterpret_cast<const float4*>(&sm.xin[r][k4]);
-                v[r] = fmaf(x.x, w0, v[r]);
-                v[r] = fmaf(x.y, w1, v[r]);
-                v[r] = fmaf(x.z, w2, v[r]);
-                v[r] = fmaf(x.w, w3, v[r]);
+              for (int r0 = 0; r0 < RT; r0 += 8) {
+                float4 x[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) x[r] = lds128(xin_a + ((r0 + r) * kPad + k4) * 4);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                  v[r0 + r] = fmaf(x[r].x, w0, v[r0 + r]);
+                  v[r0 + r] = fmaf(x[r].y, w1, v[r0 + r]);
+                  v[r0 + r] = fmaf(x[r].z, w2, v[r0 + r]);
+                  v[r0 + r] = fmaf(x[r].w, w3, v[r0 + r]);
+                }
               }
             }
 #pragma unroll
@@ -495,16 +495,22 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
               if (tid == 0) trace_ev(p, g * 4 + l - 1, 7);
 #pragma unroll
               for (int c0 = 0; c0 < RT; c0 += 32) {
-                float tmp[32];
-                tmem_ld32(taddr + c0, tmp);
+                float tmp[32], tmp2[32];
+                tmem_ld32(taddr + c0, tmp);          // W_head*A_head + W_tail*A_head
+                if (x3) {
+                  tmem_ld32(taddr + RT + c0, tmp2);  // W_head*A_tail
 #pragma unroll
-                for (int r = 0; r < 32; ++r) v[c0 + r] = tmp[r];
+                  for (int r = 0; r < 32; ++r) v[c0 + r] = tmp[r] + tmp2[r];
+                } else {
+#pragma unroll
+                  for (int r = 0; r < 32; ++r) v[c0 + r] = tmp[r];
+                }
               }
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&sm.dempty);
               ++layers;
-              const float bb = sp[kSmBigB + (l - 1) * kFTU + f];
+              const float bb = lds32(sp_a + (kSmBigB + (l - 1) * kFTU + f) * 4);
 #pragma unroll
               for (int r = 0; r < RT; ++r) v[r] = leaky(v[r] + bb);
               if (tid == 0) trace_ev(p, g * 4 + l - 1, 9);
@@ -512,16 +518,16 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
             if (l < p.n_big) {
               // ---- publish: head/tail split into the two swizzled k-chunks of the outbox ----
               if (staged > 0) mbar_wait(&sm.staging_free, (staged - 1) & 1);
-              uint8_t* ob = sm.outbox + sub * C::kAChunk;
+              const uint32_t ob = smem_u32(sm.outbox) + sub * C::kAChunk;
 #pragma unroll
               for (int r = 0; r < RT; ++r) {
                 const __nv_bfloat16 h = __float2bfloat16_rn(v[r]);
                 const __nv_bfloat16 lo = __float2bfloat16_rn(v[r] - __bfloat162float(h));
                 const uint32_t off = tile_off_bytes(r, kf);
-                *reinterpret_cast<__nv_bfloat16*>(ob + off) = h;
-                *reinterpret_cast<__nv_bfloat16*>(ob + C::kAPlane + off) = lo;
+                sts16(ob + off, __bfloat16_as_ushort(h));
+                sts16(ob + C::kAPlane + off, __bfloat16_as_ushort(lo));
               }
-              fence_proxy_async();
+              fence_proxy_async_smem();
               bar_staged_arrive_u();
               if (tid == 0) trace_ev(p, g * 4 + l, 10);
               ++staged;
@@ -532,32 +538,72 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
           if (tid == 0) trace_ev(p, g * 4 + 3, 11);
           const int pb = pxchg & 1;
           if (staged > 0) mbar_wait(&sm.staging_free, (staged - 1) & 1);
-          float* vt = reinterpret_cast<float*>(sm.outbox);  // [RT][128], float4 slots XOR-swizzled by row % 8
+          // [RT][128] fp32; float4 slot j4 of row r sits at (j4 & ~7) | ((j4 ^ (j4 >> 3) ^ ((r >> 1) << 2)) & 7): the 8
+          // lanes of a quarter warp of the reader below (4 k-quarters x 2 row pairs) then hit 8 different bank groups
+          const uint32_t vt_a = smem_u32(sm.outbox);
 #pragma unroll
-          for (int r = 0; r < RT; ++r) vt[r * kFTU + ((((f >> 2) ^ (r & 7)) << 2) | (f & 3))] = v[r];
+          for (int r = 0; r < RT; ++r)
+            sts32(vt_a + (r * kFTU + (((((f >> 2) & ~7) | (((f >> 2) ^ (f >> 5) ^ ((r >> 1) << 2)) & 7)) << 2) | (f & 3))) * 4, v[r]);
+          if (tid == 0) trace_ev(p, g * 4 + 2, 0);
           bar_epi();
+          if (tid == 0) trace_ev(p, g * 4 + 2, 1);
           {
-            float po[OPT];
+            // thread = (k quarter kq, row pair rp, output group og): 2 rows x OUTS outputs over 32 of the 128 features,
+            // then a 4-lane shuffle reduction over the k quarters
+            constexpr int OUTS = RT / 4;  // 8 (RT = 32) or 16 (RT = 64)
+            const int kq = tid & 3, rp = (tid >> 2) % (RT / 2), og = tid / (2 * RT);
+            float po[2][OUTS];
 #pragma unroll
-            for (int oo = 0; oo < OPT; ++oo) po[oo] = 0.f;
-            const float* vrow = vt + prow * kFTU;
-#pragma unroll 4
-            for (int j4 = 0; j4 < kFTU / 4; ++j4) {
-              const float4 x = *reinterpret_cast<const float4*>(vrow + ((j4 ^ (prow & 7)) << 2));
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-              for (int oo = 0; oo < OPT; ++oo) {
-                const int o = pog * OPT + oo;
-                const float4 w = *reinterpret_cast<const float4*>(sp + kSmLastW + o * kFTU + ((j4 ^ ((o >> 2) & 7)) << 2));
-                po[oo] = fmaf(x.x, w.x, po[oo]);
-                po[oo] = fmaf(x.y, w.y, po[oo]);
-                po[oo] = fmaf(x.z, w.z, po[oo]);
-                po[oo] = fmaf(x.w, w.w, po[oo]);
+              for (int oo = 0; oo < OUTS; ++oo) po[h][oo] = 0.f;
+            const uint32_t vrow = vt_a + (2 * rp) * kFTU * 4;
+            const uint32_t wrow = sp_a + (kSmLastW + og * OUTS * kFTU) * 4;
+            const int osw = (og * OUTS) >> 2;  // (o >> 2) = osw + (oo >> 2)
+#pragma unroll 2
+            for (int jj = 0; jj < 8; ++jj) {
+              const int slot = (kq << 3) | ((jj ^ kq ^ (rp << 2)) & 7);  // both rows of the pair share (row >> 1)
+              // all loads of the step first, then the FMAs (see the first layer)
+              float4 w[OUTS];
+              const float4 x0 = lds128(vrow + (slot << 4));
+              const float4 x1 = lds128(vrow + kFTU * 4 + (slot << 4));
+#pragma unroll
+              for (int oo = 0; oo < OUTS; ++oo)
+                w[oo] = lds128(wrow + (oo * kFTU + (((kq << 3) | ((jj ^ kq ^ (osw + (oo >> 2))) & 7)) << 2)) * 4);
+#pragma unroll
+              for (int oo = 0; oo < OUTS; ++oo) {
+                po[0][oo] = fmaf(x0.x, w[oo].x, po[0][oo]);
+                po[1][oo] = fmaf(x1.x, w[oo].x, po[1][oo]);
+                po[0][oo] = fmaf(x0.y, w[oo].y, po[0][oo]);
+                po[1][oo] = fmaf(x1.y, w[oo].y, po[1][oo]);
+                po[0][oo] = fmaf(x0.z, w[oo].z, po[0][oo]);
+                po[1][oo] = fmaf(x1.z, w[oo].z, po[1][oo]);
+                po[0][oo] = fmaf(x0.w, w[oo].w, po[0][oo]);
+                po[1][oo] = fmaf(x1.w, w[oo].w, po[1][oo]);
               }
             }
+            if (tid == 0) trace_ev(p, g * 4 + 2, 2);
 #pragma unroll
-            for (int oo = 0; oo < OPT; ++oo) sm.ptile[prow * kPad + pog * OPT + oo] = po[oo];
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int oo = 0; oo < OUTS; ++oo) {
+                float x = po[h][oo];
+                x += __shfl_xor_sync(0xffffffffu, x, 1);
+                x += __shfl_xor_sync(0xffffffffu, x, 2);
+                po[h][oo] = x;
+              }
+            if (kq == 0) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int o4 = 0; o4 < OUTS / 4; ++o4)
+                  sts128(smem_u32(sm.ptile) + ((2 * rp + h) * kPad + og * OUTS + 4 * o4) * 4,
+                         make_float4(po[h][4 * o4], po[h][4 * o4 + 1], po[h][4 * o4 + 2], po[h][4 * o4 + 3]));
+            }
           }
-          fence_proxy_async();
+          if (tid == 0) trace_ev(p, g * 4 + 2, 3);
+          fence_proxy_async_smem();
+          if (tid == 0) trace_ev(p, g * 4 + 2, 4);
           bar_epi();
           if (tid == 0) trace_ev(p, g * 4 + 3, 14);
           const uint32_t pexp = p.epoch + 1 + part_w[pb];
@@ -566,13 +612,13 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
               bulk_s2g(part_slot + ((size_t)pb * NT + t) * RT * kPad, sm.ptile, RT * kPad * 4);
               bulk_commit();
               bulk_wait_all();
-              st_relaxed(pflag + pb * NT + t, pexp);  // see the storer
+              st_release(pflag + pb * NT + t, pexp);  // see the storer
               trace_ev(p, g * 4 + 3, 15);
             }
             __syncwarp();
             for (int c = lane; c < NT; c += 32) wait_flag(pflag + pb * NT + c, pexp, p.status, launch_id);
             __syncwarp();
-            fence_proxy_async();
+            fence_proxy_async_smem();
             if (lane == 0) {
               // all partial tiles of the team in one copy: [NT][RT][16] fp32, over the (now dead) transposed tile
               mbar_arrive_expect_tx(&sm.pland_full, NT * RT * kPad * 4);
@@ -582,18 +628,18 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
           mbar_wait(&sm.pland_full, pxchg & 1);
           if (tid == 0) trace_ev(p, g * 4 + 3, 12);
           {
-            const float* land = reinterpret_cast<const float*>(sm.outbox);
+            const uint32_t land = smem_u32(sm.outbox);
             for (int i = tid; i < RT * 4; i += kEpiThreads) {
               const int r = i >> 2, o4 = i & 3;
-              float4 s = *reinterpret_cast<const float4*>(sp + kSmLastB + 4 * o4);
+              float4 s = lds128(sp_a + (kSmLastB + 4 * o4) * 4);
               for (int c = 0; c < NT; ++c) {  // fixed order: bitwise identical replicas
-                const float4 x = *reinterpret_cast<const float4*>(land + ((size_t)c * RT + r) * kPad + 4 * o4);
+                const float4 x = lds128(land + ((c * RT + r) * kPad + 4 * o4) * 4);
                 s.x += x.x;
                 s.y += x.y;
                 s.z += x.z;
                 s.w += x.w;
               }
-              *reinterpret_cast<float4*>(&sm.a[r][4 * o4]) = s;
+              sts128(smem_u32(&sm.a[r][4 * o4]), s);
             }
           }
           __syncwarp();

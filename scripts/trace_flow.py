@@ -21,7 +21,7 @@ poses = robot.forward_kinematics(robot.sample_joint_angles(batch, generator=g))
 for _ in range(3):
     solver.generate_ik_solutions(poses, latent=latent)
 torch.cuda.synchronize()
-nl = 120
+nl = 24
 NT = 16
 stamps = torch.zeros(NT * nl * 16, dtype=torch.int64, device="cuda")
 h = solver.nn_model._handle(torch.device("cuda", 0))
@@ -43,8 +43,7 @@ for layer, ev, nm in [(1, 7, "full0"), (1, 8, "mma end"), (1, 5, "flag"), (3, 11
     print(f"layer {layer} {nm:>10s}: " + " ".join(f"{(int(v) - t0) / 1000.0:7.2f}" for v in sa[:, layer, ev]))
 
 
-print("per-chunk stamps, layer 1 of CTA 0 (us): loader [reach, stage free, issued(+8=W only)]  mma [reach, full, committed]")
-for i in range(16):
-    r = sa[0, 100 + i]
-    f = lambda v: (int(v) - t0) / 1000.0 if v > 0 else float("nan")
-    print(f"chunk {i:2d}: L {f(r[0]):7.2f} {f(r[1]):7.2f} {f(r[2]):7.2f} {f(r[10]):7.2f} | M {f(r[3]):7.2f} {f(r[4]):7.2f} {f(r[5]):7.2f}")
+
+print("dot phase detail (row 4g+2): vt stored, bar passed, dot loop done, shuffles+ptile done, fence done")
+for i in (2, 6, 10):
+    print(i, " ".join(f"{(int(v) - t0) / 1000.0:8.2f}" for v in sa[0, i, :5]))

@@ -205,3 +205,27 @@ def test_fast_bf16x1_mode_reports_its_error_honestly():
     out = model.inverse(latent.to(DEV), cond.to(DEV))
     err = (out.cpu() - _oracle(sd, hp, latent, cond)).abs().max().item()
     assert 1e-4 < err < 0.2, err  # NOT parity grade: single bf16 products
+
+
+@pytest.mark.parametrize("engine", ["umma", "mma"])
+def test_repeated_calls_are_bitwise_identical_under_load(engine, monkeypatch):
+    """The engines are deterministic (fixed accumulation and summation orders), so any difference between repeated
+    calls is a synchronisation bug in the inter-CTA exchange (e.g. a flag published before its data is visible)."""
+    monkeypatch.setenv("IKFLOW_B200_ENGINE", engine)
+    hp = IkflowModelParameters()
+    hp.nb_nodes, hp.dim_latent_space = 12, 7
+    robot = ikflow_b200.Panda()
+    model = ikflow_b200.glow_cNF_model(hp, robot, 8, 7)
+    model.load_state_dict(make_synthetic_state_dict(hp, robot.actuated_joints_limits, seed=0))
+    latent, poses, cond = _inputs(512, 7)
+    latent, cond = latent.to(DEV), cond.to(DEV)
+    flush = torch.empty(300 << 20, dtype=torch.uint8, device=DEV)
+    ref = model.inverse(latent, cond).clone()
+    assert (ref.cpu() - _oracle(make_synthetic_state_dict(hp, robot.actuated_joints_limits, seed=0), hp, latent.cpu(), cond.cpu())).abs().max() < TOL
+    differing = 0
+    for i in range(300):
+        if i % 3 == 0:
+            flush.fill_(i & 255)
+        differing += int(not torch.equal(model.inverse(latent, cond), ref))
+    assert differing == 0
+    assert model.status() == 0
