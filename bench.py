@@ -132,14 +132,6 @@ class ClockSampler:
         }
 
 
-def build_inputs(robot_name: str, batch: int, width: int, seed: int):
-    """Synthetic, reachable target poses: q ~ U(limits) -> FK (oracle-free: the package's own FK kernel on the GPU,
-    or a torch fallback for the CPU arm)."""
-    g = torch.Generator().manual_seed(seed)
-    latent = torch.randn(batch, width, generator=g)
-    return g, latent
-
-
 def cpu_reference_arm(model_name: str, batch: int, steps: int, warmup: int, budget_s: float):
     """The reference's own torch path restated (oracle/), on the host cores."""
     from ikflow_b200.model import IkflowModelParameters, make_synthetic_state_dict
@@ -334,13 +326,13 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"], "traffic": 205_143_808 + 4_329_984 if args.model == "panda__full__lp191_5.25m" and B == 512 else None,
+                "frac": achieved / peaks["bf16_tflops"], "traffic": 205_156_352 + 3_525_120 if args.model == "panda__full__lp191_5.25m" and B == 512 else None,
                 "peak_source": peaks["source"] + ", burst bf16",
-                "kernel": "ikf::flow_inverse_kernel", "kernel_ms": kernel_ms,
+                "kernel": "ikf::umma::flow_inverse_umma_kernel<32>" if B <= 576 else "ikf::umma::flow_inverse_umma_kernel<64>", "kernel_ms": kernel_ms,
                 "algorithmic_flops_per_launch": fl * B,
                 "hbm": {"algorithmic_bytes_per_launch": wbytes + B * 84, "achieved_gbs": (wbytes + B * 84) / (kernel_ms * 1e-3) / 1e9,
                         "peak_gbs": peaks["hbm_gbs"], "frac": (wbytes + B * 84) / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-                "traffic_note": "dram__bytes_read+write of one launch, profiles/ (ncu --set full)",
+                "traffic_note": "dram__bytes_read+write of one launch, profiles/r1_flow_umma_b512_ncu_summary.txt (ncu --set full)",
             },
             "status_word": status,
         }
