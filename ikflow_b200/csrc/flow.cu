@@ -86,7 +86,7 @@ struct IkfFlow {
   void* blob = nullptr;  // one device allocation holding everything below
   size_t blob_bytes = 0, big_w_bytes = 0;
   ikf::FlowParams base;  // pointers + model constants; per-call fields filled at launch
-  size_t smem32 = 0, smem64 = 0;
+  size_t smem32 = 0, smem64 = 0, smem128 = 0;
   int engine = 0;  // 0 = mma.sync tiles (flow_mma.cuh), 1 = tcgen05 / TMEM (flow_umma.cuh)
   uint32_t epoch = 1;  // doubles as launch id; 0 is "no launch aborted"
   int last_grid = 0;
@@ -270,7 +270,7 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   const size_t off_act = align_up(off_consts + consts.size() * 4);
   const size_t act_bytes = (size_t)slots * 2 * NT * (engine ? umma::kAStrideU : kAChunkStride);
   const size_t off_partial = align_up(off_act + act_bytes);
-  const size_t partial_bytes = (size_t)slots * 2 * NT * kRTMax * kPad * 4;
+  const size_t partial_bytes = (size_t)slots * 2 * NT * (engine ? umma::kRTMaxU : kRTMax) * kPad * 4;
   const size_t off_flags = align_up(off_partial + partial_bytes);
   const size_t flag_bytes = ((size_t)slots * 2 * NT * 2 + 2) * 4;
   f->blob_bytes = align_up(off_flags + flag_bytes);
@@ -289,6 +289,7 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   if (engine) {
     f->smem32 = sizeof(umma::Smem<32>) + 1024;
     f->smem64 = sizeof(umma::Smem<64>) + 1024;
+    f->smem128 = sizeof(umma::Smem<128>) + 1024;
   } else {
     f->smem32 = sizeof(FlowSmem<32>) + 1024;
     f->smem64 = sizeof(FlowSmem<64>) + 1024;
@@ -296,16 +297,21 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   f->smem_bytes = f->smem64;
   const void* k32 = engine ? (const void*)umma::flow_inverse_umma_kernel<32> : (const void*)flow_inverse_kernel<32>;
   const void* k64 = engine ? (const void*)umma::flow_inverse_umma_kernel<64> : (const void*)flow_inverse_kernel<64>;
-  const int threads = engine ? umma::kThreadsU : kThreads;
+  const int threads32 = engine ? umma::Cfg<32>::kThreads : kThreads;
+  const int threads64 = engine ? umma::Cfg<64>::kThreads : kThreads;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem32);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem64);
+  if (e == cudaSuccess && engine)
+    e = cudaFuncSetAttribute(umma::flow_inverse_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem128);
   if (e == cudaSuccess) {
     // the teams spin on each other's flags, so every CTA of a launch must be resident: size the slot count from
     // what the device really fits
-    int occ32 = 0, occ64 = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, k32, threads, f->smem32);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, k64, threads, f->smem64);
-    const int occ = std::min(occ32, occ64);
+    int occ32 = 0, occ64 = 0, occ128 = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, k32, threads32, f->smem32);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, k64, threads64, f->smem64);
+    if (e == cudaSuccess && engine)
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ128, umma::flow_inverse_umma_kernel<128>, umma::Cfg<128>::kThreads, f->smem128);
+    const int occ = std::min(std::min(occ32, occ64), occ128);
     if (e == cudaSuccess && occ < 1) {
       ikf_flow_destroy(f);
       return fail(IKF_EDEVICE, "ikf_flow_create: the flow kernel does not fit on an SM of device %d", device);
@@ -367,7 +373,13 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   p.block_first = block_first; p.block_last = block_last; p.finalize = finalize; p.clamp_out = clamp;
   // Row groups of 32 while that still fits in one wave of teams (more CTAs in flight, and a partner CTA on every SM
   // to compute while a team waits on an exchange), 64 beyond.
-  const int rt = ((batch + 31) / 32 <= flow->slots_max) ? 32 : 64;
+  int rt = ((batch + 31) / 32 <= flow->slots_max) ? 32 : 64;
+  // umma engine: 128-row groups once 64-row groups would need more than one wave (twice the rows per weight byte)
+  if (flow->engine && (batch + 63) / 64 > flow->slots_max) rt = 128;
+  if (const char* env = std::getenv("IKFLOW_B200_RT")) {  // debugging / A-B comparisons
+    const int v = std::atoi(env);
+    if (v == 32 || v == 64 || (v == 128 && flow->engine)) rt = v;
+  }
   p.n_rowgroups = (batch + rt - 1) / rt;
   p.slots = std::min(p.n_rowgroups, flow->slots_max);
   p.epoch = flow->epoch;
@@ -382,10 +394,20 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   void* args[] = {(void*)&p};
   // cooperative launch = the driver guarantees that all CTAs of all teams are co-resident (the teams spin on each
   // other's flags)
-  const void* fn = flow->engine ? (rt == 32 ? (const void*)umma::flow_inverse_umma_kernel<32> : (const void*)umma::flow_inverse_umma_kernel<64>)
-                                : (rt == 32 ? (const void*)flow_inverse_kernel<32> : (const void*)flow_inverse_kernel<64>);
-  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(flow->engine ? umma::kThreadsU : kThreads), args,
-                                              rt == 32 ? flow->smem32 : flow->smem64, (cudaStream_t)stream);
+  const void* fn;
+  int threads;
+  size_t smem;
+  if (flow->engine) {
+    fn = rt == 32 ? (const void*)umma::flow_inverse_umma_kernel<32>
+                  : rt == 64 ? (const void*)umma::flow_inverse_umma_kernel<64> : (const void*)umma::flow_inverse_umma_kernel<128>;
+    threads = rt == 32 ? umma::Cfg<32>::kThreads : rt == 64 ? umma::Cfg<64>::kThreads : umma::Cfg<128>::kThreads;
+    smem = rt == 32 ? flow->smem32 : rt == 64 ? flow->smem64 : flow->smem128;
+  } else {
+    fn = rt == 32 ? (const void*)flow_inverse_kernel<32> : (const void*)flow_inverse_kernel<64>;
+    threads = kThreads;
+    smem = rt == 32 ? flow->smem32 : flow->smem64;
+  }
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, (cudaStream_t)stream);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return fail(IKF_ECUDA, "%s: launch failed: %s", name, cudaGetErrorString(e));
   return IKF_OK;

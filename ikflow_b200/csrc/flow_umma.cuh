@@ -21,17 +21,12 @@ namespace umma {
 constexpr int kFTU = 128;                       // hidden features per CTA
 constexpr int kWPlaneU = kFTU * kKC * 2;        // one bf16 plane of a weight chunk [128][64]: 16 KB
 constexpr int kWChunkU = 2 * kWPlaneU;          // head + tail: 32 KB
-constexpr int kAStrideU = 2 * 2 * kRTMax * kKC * 2;  // scratch bytes reserved per producer: 2 k-chunks x (head+tail): 32 KB
-constexpr int kEpiWarps = 4;
-constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kRTMaxU = 128;                          // largest row group of this engine
+constexpr int kAStrideU = 2 * 2 * kRTMaxU * kKC * 2;  // scratch bytes reserved per producer: 2 k-chunks x (head+tail): 64 KB
 // One bulk copy keeps its issuing thread busy for ~0.3-0.45 us whatever its size; copies issued by different warps run
 // concurrently (scripts/ubench/ingest2.cu).  Four loader warps take the k-chunks round robin so that four copies are
 // always being issued.
 constexpr int kLoaderWarps = 4;
-constexpr int kLoaderWarpU = kEpiWarps;  // first loader warp
-constexpr int kMmaWarpU = kEpiWarps + kLoaderWarps;
-constexpr int kStorerWarpU = kMmaWarpU + 1;
-constexpr int kThreadsU = (kStorerWarpU + 1) * 32;
 // per (subnet, feature tile) small fp32 parameters:
 //   first_wT [16 k][128 f] | first_b [128] | big_b [kMaxBig][128] | last_w [16 o][128 f] (float4 slots swizzled, see
 //   flow.cu) | last_b [16]
@@ -49,15 +44,24 @@ struct Cfg {
   static constexpr int kAPlane = RT * kKC * 2;       // one bf16 plane of an activation k-chunk [RT][64]
   static constexpr int kAChunk = 2 * kAPlane;        // head + tail
   static constexpr int kStage = kWChunkU + kAChunk;  // 40 KB (RT=32) / 48 KB (RT=64)
+  // Epilogue threads: 128 per group (thread = TMEM lane = hidden feature); a group drains EPI_ROWS accumulator columns.
+  // RT = 128 uses two groups (rows 0-63 and 64-127) that share the outbox one after the other.
+  static constexpr int kGroups = RT > 64 ? 2 : 1;
+  static constexpr int kEpiRows = RT / kGroups;
+  static constexpr int kEpiWarps = 4 * kGroups;
+  static constexpr int kEpiThreads = 32 * kEpiWarps;
+  static constexpr int kLoaderWarp0 = kEpiWarps;  // first loader warp
+  static constexpr int kMmaWarp = kEpiWarps + kLoaderWarps;
+  static constexpr int kStorerWarp = kMmaWarp + 1;
+  static constexpr int kThreads = (kStorerWarp + 1) * 32;
   static constexpr int kStages = RT == 32 ? 4 : 2;
   // loader warp w owns the ring stages s with s % kLoaders == w: its waits on a stage's barriers are then strictly in
   // order (a waiter may lag an mbarrier by at most one phase)
   static constexpr int kLoaders = kStages < kLoaderWarps ? kStages : kLoaderWarps;
   static_assert(kStages % kLoaders == 0, "every stage needs exactly one owner");
-  static constexpr int kOutbox = 2 * kAChunk;        // the CTA's 128 features = two k-chunks; = RT*512 bytes
+  static constexpr int kHalfPlane = kEpiRows * kKC * 2;  // one bf16 plane of one k-chunk for the rows of one group
+  static constexpr int kOutbox = 4 * kHalfPlane;         // [k-chunk 2][head|tail][kEpiRows][64 k] = kEpiRows*512 bytes
   static constexpr int kTmemCols = 2 * RT <= 32 ? 32 : (2 * RT <= 64 ? 64 : (2 * RT <= 128 ? 128 : 256));  // D[:, 0:2RT]
-  static constexpr int kOutPerThread = RT / 8;       // last-layer outputs per epilogue thread (RT*16 / 128)
-  static constexpr int kThreadsPerRow = 16 / kOutPerThread;
   static_assert(kStage % 1024 == 0, "stages must keep the 1024-byte alignment of the swizzle atoms");
 };
 
@@ -65,18 +69,18 @@ template <int RT>
 struct __align__(1024) Smem {
   using C = Cfg<RT>;
   uint8_t ring[C::kStages][C::kStage];  // [weights head|tail][activations head|tail]
-  // publish staging (two swizzled bf16 k-chunks)  |  fp32 activations [RT][128] for the last layer  |  landing zone of
-  // the team's partial tiles [NT][RT][16]
+  // publish staging of one epilogue group (two swizzled bf16 k-chunks)  |  its fp32 activations [kEpiRows][128] for the
+  // last layer
   uint8_t outbox[C::kOutbox];
   float ptile[RT * kPad];  // this CTA's partial sums of the last layer
   float small[2][kSmallFloatsU];
-  float u[RT][kPad];    // flow state
-  float xin[RT][kPad];  // input of the current subnet: [state half | condition | 0]
+  float u[RT][kPad];  // flow state
   float cnd[RT][8];
-  float a[RT][kPad];    // output of the last layer of the current subnet
+  // input of the current subnet [state half | condition | 0] at its start, output of its last layer at its end
+  float a[RT][kPad];
   uint64_t full[C::kStages], empty[C::kStages];
   uint64_t small_full[2], small_empty[2];
-  uint64_t staging_free, dfull, dempty, pland_full;
+  uint64_t staging_free, dfull, dempty;
   uint32_t tmem_base;
 };
 
@@ -173,18 +177,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
-__device__ __forceinline__ void bar_staged_arrive_u() {
-  asm volatile("bar.arrive 2, %0;" ::"n"(kEpiThreads + 32) : "memory");
-}
-__device__ __forceinline__ void bar_staged_sync_u() {
-  asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads + 32) : "memory");
-}
+template <int N>
+__device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
+// one epilogue group (128 threads) + the storer warp: "the outgoing chunk is staged"
+__device__ __forceinline__ void bar_staged_arrive_u() { asm volatile("bar.arrive 2, %0;" ::"n"(128 + 32) : "memory"); }
+__device__ __forceinline__ void bar_staged_sync_u() { asm volatile("bar.sync 2, %0;" ::"n"(128 + 32) : "memory"); }
 
 template <int RT>
-__global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const FlowParams p) {
+__global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel(const FlowParams p) {
   using C = Cfg<RT>;
   constexpr int kStages = C::kStages;
+  constexpr int G = C::kGroups, ER = C::kEpiRows, ET = C::kEpiThreads;
   extern __shared__ uint8_t smem_raw[];
   Smem<RT>& sm = *reinterpret_cast<Smem<RT>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -204,16 +207,15 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sm.small_full[b], 1);
-      mbar_init(&sm.small_empty[b], kEpiWarps);
+      mbar_init(&sm.small_empty[b], C::kEpiWarps);
     }
     mbar_init(&sm.staging_free, 1);
     mbar_init(&sm.dfull, 1);
-    mbar_init(&sm.dempty, kEpiWarps);
-    mbar_init(&sm.pland_full, 1);
+    mbar_init(&sm.dempty, C::kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
-  if (warp == kMmaWarpU) {
+  if (warp == C::kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)),
                  "n"(C::kTmemCols)
                  : "memory");
@@ -225,7 +227,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
   const uint32_t tmem = sm.tmem_base;
 
   uint8_t* act_slot = p.act + (size_t)slot * 2 * NT * kAStrideU;
-  float* part_slot = p.partial + (size_t)slot * 2 * NT * kRTMax * kPad;
+  float* part_slot = p.partial + (size_t)slot * 2 * NT * kRTMaxU * kPad;
   uint32_t* aflag = p.act_flag + (size_t)slot * 2 * NT;
   uint32_t* pflag = p.part_flag + (size_t)slot * 2 * NT;
 
@@ -234,12 +236,12 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
   const int my_rgs = (p.n_rowgroups - slot + p.slots - 1) / p.slots;
   const int total_steps = my_rgs * steps_per_rg;
 
-  if (warp >= kLoaderWarpU && warp < kLoaderWarpU + kLoaderWarps) {
+  if (warp >= C::kLoaderWarp0 && warp < C::kLoaderWarp0 + kLoaderWarps) {
     // ===== loaders: bulk-TMA producers.  k-chunk number pos = ring_pos + i (counted over the whole launch) goes to ring
     // stage pos % kStages and is loaded by loader warp pos % kLoaders; warp 0 also prefetches the small parameters and
     // pulls the next layer's weights into L2.  Chunks are consumed in the fixed order kc = (2t + i) % KCH, so the
     // accumulation order never depends on timing.
-    const int lw = warp - kLoaderWarpU;
+    const int lw = warp - C::kLoaderWarp0;
     uint32_t ring_pos = 0;
     uint32_t act_w[2] = {0, 0};
     uint32_t xchg = 0;
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
       }
       if (lw == 0 && p.n_big == 0) prefetch_small(g + 1);
     }
-  } else if (warp == kMmaWarpU) {
+  } else if (warp == C::kMmaWarp) {
     // ===== MMA issuer: one thread drives the tensor core =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kFTU, RT);       // N = RT
@@ -384,48 +386,59 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
         }
       }
     }
-  } else if (warp == kStorerWarpU) {
-    // ===== storer: publishes this CTA's 128 features (two k-chunks) to the team =====
+  } else if (warp == C::kStorerWarp) {
+    // ===== storer: publishes this CTA's 128 features (two k-chunks) to the team, one epilogue group at a time =====
+    // scratch layout of a producer: [k-chunk 2][head|tail][RT rows][64 k]; a group contributes ER rows of each plane,
+    // i.e. four regions of kHalfPlane bytes, stored by four lanes at once
     uint32_t act_w[2] = {0, 0};
     uint32_t xchg = 0;
     for (int g = 0; g < total_steps; ++g) {
       for (int l = 0; l < p.n_big; ++l) {
         const int buf = xchg & 1;
-        bar_staged_sync_u();
-        if (lane == 0) {
-          uint8_t* dst = act_slot + ((size_t)buf * NT + t) * kAStrideU;
-          trace_ev(p, g * 4 + l, 3);
-          bulk_s2g(dst, sm.outbox, C::kOutbox);
-          bulk_commit();
-          bulk_wait_all();
-          trace_ev(p, g * 4 + l, 4);
-          // The release is NOT optional: completion of the bulk store (wait_group) makes its bytes visible to this
-          // thread only.  A relaxed flag store here lets consumers read stale chunks (scripts/stress_flow.py: 37 of
-          // 1500 calls differ); the MEMBAR.GPU of st.release costs ~1 us per exchange.
-          st_release(aflag + buf * NT + t, p.epoch + 1 + act_w[buf]);
-          trace_ev(p, g * 4 + l, 5);
-          mbar_arrive(&sm.staging_free);
+        for (int hh = 0; hh < G; ++hh) {
+          bar_staged_sync_u();  // the group has written + proxy-fenced the outbox
+          if (lane == 0) trace_ev(p, g * 4 + l, 3);
+          if (lane < 4) {
+            uint8_t* dst = act_slot + ((size_t)buf * NT + t) * kAStrideU + (size_t)lane * C::kAPlane + (size_t)hh * C::kHalfPlane;
+            bulk_s2g(dst, sm.outbox + lane * C::kHalfPlane, C::kHalfPlane);
+            bulk_commit();
+            bulk_wait_all();
+          }
+          __syncwarp();
+          if (lane == 0) {
+            trace_ev(p, g * 4 + l, 4);
+            // The release is NOT optional: completion of a bulk store (wait_group) makes its bytes visible to the
+            // issuing thread only.  A relaxed flag store here lets consumers read stale chunks
+            // (scripts/stress_flow.py: 37 of 1500 calls differed); the MEMBAR.GPU of st.release costs ~1 us per exchange.
+            if (hh == G - 1) st_release(aflag + buf * NT + t, p.epoch + 1 + act_w[buf]);
+            trace_ev(p, g * 4 + l, 5);
+            mbar_arrive(&sm.staging_free);
+          }
+          __syncwarp();
         }
-        __syncwarp();
         ++act_w[buf];
         ++xchg;
       }
     }
   } else {
-    // ===== epilogue / SIMT warps: thread f owns hidden feature 128 t + f (TMEM lane f) =====
-    const int f = tid;
-    const int sub = f >> 6;  // which of the CTA's two 64-wide k-chunks
+    // ===== epilogue / SIMT warps: thread (f, h) owns hidden feature 128 t + f (TMEM lane f) for the rows of group h =====
+    const int f = tid & 127;
+    const int h = tid >> 7;    // epilogue group: rows h*ER .. h*ER + ER - 1
+    const int sub = f >> 6;    // which of the CTA's two 64-wide k-chunks
     const int kf = f & 63;
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    const int row0 = h * ER;
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t part_w[2] = {0, 0};
     uint32_t pxchg = 0;
-    uint32_t staged = 0;
-    uint32_t layers = 0;  // hidden layers drained so far
+    uint32_t pubs = 0;     // uses of the outbox handed to the storer so far (all groups count all uses)
+    uint32_t layers = 0;   // hidden layers drained so far
     const bool x3 = p.precision == IKF_PRECISION_BF16X3;
+    const uint32_t outbox_a = smem_u32(sm.outbox);
+    const uint32_t xin_a = smem_u32(&sm.a[0][0]);
 
     int g = 0;
     for (int rg = slot; rg < p.n_rowgroups; rg += p.slots) {
-      for (int i = tid; i < RT * kPad; i += kEpiThreads) {
+      for (int i = tid; i < RT * kPad; i += ET) {
         const int r = i / kPad, j = i % kPad;
         const int row = rg * RT + r;
         float uv = 0.f, cv = 0.f;
@@ -436,43 +449,41 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
         sm.u[r][j] = uv;
         if (j < 8) sm.cnd[r][j] = cv;
       }
-      bar_epi();
+      bar_epi<ET>();
 
       for (int blk = p.block_first; blk >= p.block_last; --blk) {
         for (int sidx = 0; sidx < 2; ++sidx, ++g) {
           const int sb = g & 1;
-          const float* sp = sm.small[sb];
           const uint32_t sp_a = smem_u32(sm.small[sb]);  // explicit shared-space accesses (see lds128)
           const int in_off = sidx == 0 ? 0 : p.s1;
           const int in_len = sidx == 0 ? p.s1 : p.s2;
           const int tg_off = sidx == 0 ? p.s1 : 0;
           const int tg_len = sidx == 0 ? p.s2 : p.s1;
           const int kin = in_len + p.dim_cond;
-          // subnet input [state half | condition]
-          for (int i = tid; i < RT * kPad; i += kEpiThreads) {
+          // subnet input [state half | condition | 0] (sm.a doubles as this buffer until the last layer)
+          for (int i = tid; i < RT * kPad; i += ET) {
             const int r = i / kPad, k = i % kPad;
-            sm.xin[r][k] = k < in_len ? sm.u[r][in_off + k] : (k < kin ? sm.cnd[r][k - in_len] : 0.f);
+            sm.a[r][k] = k < in_len ? sm.u[r][in_off + k] : (k < kin ? sm.cnd[r][k - in_len] : 0.f);
           }
           mbar_wait(&sm.small_full[sb], (g >> 1) & 1);
-          bar_epi();
+          bar_epi<ET>();
 
-          float v[RT];  // activations of feature f for the RT rows
+          float v[ER];  // activations of feature f for the rows of this group
           // ---- first layer: fp32 FMA ----
           {
             const float b0 = lds32(sp_a + (kSmFirstB + f) * 4);
 #pragma unroll
-            for (int r = 0; r < RT; ++r) v[r] = b0;
-            const uint32_t xin_a = smem_u32(&sm.xin[0][0]);
-            for (int k4 = 0; k4 < kin; k4 += 4) {  // xin is zero-padded to 16 columns, the weights too
+            for (int r = 0; r < ER; ++r) v[r] = b0;
+            for (int k4 = 0; k4 < kin; k4 += 4) {  // the input is zero-padded to 16 columns, the weights too
               const uint32_t wa = sp_a + (kSmFirstW + k4 * kFTU + f) * 4;
               const float w0 = lds32(wa), w1 = lds32(wa + kFTU * 4), w2 = lds32(wa + 2 * kFTU * 4), w3 = lds32(wa + 3 * kFTU * 4);
-              // only four warps run this and every one is alone on its scheduler: issue the loads of 8 rows back to
-              // back, then the 32 FMAs that consume them, so that the shared-memory latency is paid once per batch
+              // every epilogue warp is alone on its scheduler: issue the loads of 8 rows back to back, then the 32 FMAs
+              // that consume them, so that the shared-memory latency is paid once per batch
 #pragma unroll
-              for (int r0 = 0; r0 < RT; r0 += 8) {
+              for (int r0 = 0; r0 < ER; r0 += 8) {
                 float4 x[8];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) x[r] = lds128(xin_a + ((r0 + r) * kPad + k4) * 4);
+                for (int r = 0; r < 8; ++r) x[r] = lds128(xin_a + ((row0 + r0 + r) * kPad + k4) * 4);
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                   v[r0 + r] = fmaf(x[r].x, w0, v[r0 + r]);
@@ -483,7 +494,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
               }
             }
 #pragma unroll
-            for (int r = 0; r < RT; ++r) v[r] = leaky(v[r]);
+            for (int r = 0; r < ER; ++r) v[r] = leaky(v[r]);
           }
 
           for (int l = 0; l <= p.n_big; ++l) {
@@ -494,11 +505,11 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
               tc_fence_after();
               if (tid == 0) trace_ev(p, g * 4 + l - 1, 7);
 #pragma unroll
-              for (int c0 = 0; c0 < RT; c0 += 32) {
+              for (int c0 = 0; c0 < ER; c0 += 32) {
                 float tmp[32], tmp2[32];
-                tmem_ld32(taddr + c0, tmp);          // W_head*A_head + W_tail*A_head
+                tmem_ld32(taddr + row0 + c0, tmp);  // W_head*A_head + W_tail*A_head
                 if (x3) {
-                  tmem_ld32(taddr + RT + c0, tmp2);  // W_head*A_tail
+                  tmem_ld32(taddr + RT + row0 + c0, tmp2);  // W_head*A_tail
 #pragma unroll
                   for (int r = 0; r < 32; ++r) v[c0 + r] = tmp[r] + tmp2[r];
                 } else {
@@ -512,100 +523,106 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
               ++layers;
               const float bb = lds32(sp_a + (kSmBigB + (l - 1) * kFTU + f) * 4);
 #pragma unroll
-              for (int r = 0; r < RT; ++r) v[r] = leaky(v[r] + bb);
+              for (int r = 0; r < ER; ++r) v[r] = leaky(v[r] + bb);
               if (tid == 0) trace_ev(p, g * 4 + l - 1, 9);
             }
             if (l < p.n_big) {
-              // ---- publish: head/tail split into the two swizzled k-chunks of the outbox ----
-              if (staged > 0) mbar_wait(&sm.staging_free, (staged - 1) & 1);
-              const uint32_t ob = smem_u32(sm.outbox) + sub * C::kAChunk;
+              // ---- publish: head/tail split into the swizzled planes of the outbox, one group after the other ----
 #pragma unroll
-              for (int r = 0; r < RT; ++r) {
-                const __nv_bfloat16 h = __float2bfloat16_rn(v[r]);
-                const __nv_bfloat16 lo = __float2bfloat16_rn(v[r] - __bfloat162float(h));
-                const uint32_t off = tile_off_bytes(r, kf);
-                sts16(ob + off, __bfloat16_as_ushort(h));
-                sts16(ob + C::kAPlane + off, __bfloat16_as_ushort(lo));
+              for (int hh = 0; hh < G; ++hh) {
+                if (h == hh) {
+                  if (pubs > 0) mbar_wait(&sm.staging_free, (pubs - 1) & 1);
+                  const uint32_t ob = outbox_a + sub * 2 * C::kHalfPlane;
+#pragma unroll
+                  for (int r = 0; r < ER; ++r) {
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(v[r]);
+                    const __nv_bfloat16 lo = __float2bfloat16_rn(v[r] - __bfloat162float(hi));
+                    const uint32_t off = tile_off_bytes(r, kf);  // (row0 + r) & 7 == r & 7: ER is a multiple of 8
+                    sts16(ob + off, __bfloat16_as_ushort(hi));
+                    sts16(ob + C::kHalfPlane + off, __bfloat16_as_ushort(lo));
+                  }
+                  fence_proxy_async_smem();
+                  bar_staged_arrive_u();
+                }
+                ++pubs;
               }
-              fence_proxy_async_smem();
-              bar_staged_arrive_u();
               if (tid == 0) trace_ev(p, g * 4 + l, 10);
-              ++staged;
             }
           }
 
-          // ---- last layer: fp32, through a transposed copy of the activations ----
+          // ---- last layer: fp32, through a transposed copy of the activations (one group at a time) ----
           if (tid == 0) trace_ev(p, g * 4 + 3, 11);
           const int pb = pxchg & 1;
-          if (staged > 0) mbar_wait(&sm.staging_free, (staged - 1) & 1);
-          // [RT][128] fp32; float4 slot j4 of row r sits at (j4 & ~7) | ((j4 ^ (j4 >> 3) ^ ((r >> 1) << 2)) & 7): the 8
-          // lanes of a quarter warp of the reader below (4 k-quarters x 2 row pairs) then hit 8 different bank groups
-          const uint32_t vt_a = smem_u32(sm.outbox);
+          if (pubs > 0) mbar_wait(&sm.staging_free, (pubs - 1) & 1);  // the storer is done with the outbox
 #pragma unroll
-          for (int r = 0; r < RT; ++r)
-            sts32(vt_a + (r * kFTU + (((((f >> 2) & ~7) | (((f >> 2) ^ (f >> 5) ^ ((r >> 1) << 2)) & 7)) << 2) | (f & 3))) * 4, v[r]);
-          if (tid == 0) trace_ev(p, g * 4 + 2, 0);
-          bar_epi();
-          if (tid == 0) trace_ev(p, g * 4 + 2, 1);
-          {
-            // thread = (k quarter kq, row pair rp, output group og): 2 rows x OUTS outputs over 32 of the 128 features,
-            // then a 4-lane shuffle reduction over the k quarters
-            constexpr int OUTS = RT / 4;  // 8 (RT = 32) or 16 (RT = 64)
-            const int kq = tid & 3, rp = (tid >> 2) % (RT / 2), og = tid / (2 * RT);
-            float po[2][OUTS];
+          for (int hh = 0; hh < G; ++hh) {
+            // [ER][128] fp32; float4 slot j4 of row r sits at (j4 & ~7) | ((j4 ^ (j4 >> 3) ^ ((r >> 1) << 2)) & 7): the 8
+            // lanes of a quarter warp of the reader below (4 k-quarters x 2 row pairs) then hit 8 different bank groups
+            if (h == hh) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+              for (int r = 0; r < ER; ++r)
+                sts32(outbox_a + (r * kFTU + (((((f >> 2) & ~7) | (((f >> 2) ^ (f >> 5) ^ ((r >> 1) << 2)) & 7)) << 2) | (f & 3))) * 4, v[r]);
+            }
+            bar_epi<ET>();
+            if (h == hh) {
+              // thread = (k quarter kq, row pair rp, output group og): 2 rows x OUTS outputs over 32 of the 128
+              // features, then a 4-lane shuffle reduction over the k quarters
+              constexpr int OUTS = ER / 4;  // 8 (ER = 32) or 16 (ER = 64)
+              const int kq = f & 3, rp = (f >> 2) % (ER / 2), og = f / (2 * ER);
+              float po[2][OUTS];
 #pragma unroll
-              for (int oo = 0; oo < OUTS; ++oo) po[h][oo] = 0.f;
-            const uint32_t vrow = vt_a + (2 * rp) * kFTU * 4;
-            const uint32_t wrow = sp_a + (kSmLastW + og * OUTS * kFTU) * 4;
-            const int osw = (og * OUTS) >> 2;  // (o >> 2) = osw + (oo >> 2)
+              for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int oo = 0; oo < OUTS; ++oo) po[q][oo] = 0.f;
+              const uint32_t vrow = outbox_a + (2 * rp) * kFTU * 4;
+              const uint32_t wrow = sp_a + (kSmLastW + og * OUTS * kFTU) * 4;
+              const int osw = (og * OUTS) >> 2;  // (o >> 2) = osw + (oo >> 2)
 #pragma unroll 2
-            for (int jj = 0; jj < 8; ++jj) {
-              const int slot = (kq << 3) | ((jj ^ kq ^ (rp << 2)) & 7);  // both rows of the pair share (row >> 1)
-              // all loads of the step first, then the FMAs (see the first layer)
-              float4 w[OUTS];
-              const float4 x0 = lds128(vrow + (slot << 4));
-              const float4 x1 = lds128(vrow + kFTU * 4 + (slot << 4));
+              for (int jj = 0; jj < 8; ++jj) {
+                const int slot_ = (kq << 3) | ((jj ^ kq ^ (rp << 2)) & 7);  // both rows of the pair share (row >> 1)
+                // all loads of the step first, then the FMAs (see the first layer)
+                float4 w[OUTS];
+                const float4 x0 = lds128(vrow + (slot_ << 4));
+                const float4 x1 = lds128(vrow + kFTU * 4 + (slot_ << 4));
 #pragma unroll
-              for (int oo = 0; oo < OUTS; ++oo)
-                w[oo] = lds128(wrow + (oo * kFTU + (((kq << 3) | ((jj ^ kq ^ (osw + (oo >> 2))) & 7)) << 2)) * 4);
+                for (int oo = 0; oo < OUTS; ++oo)
+                  w[oo] = lds128(wrow + (oo * kFTU + (((kq << 3) | ((jj ^ kq ^ (osw + (oo >> 2))) & 7)) << 2)) * 4);
 #pragma unroll
-              for (int oo = 0; oo < OUTS; ++oo) {
-                po[0][oo] = fmaf(x0.x, w[oo].x, po[0][oo]);
-                po[1][oo] = fmaf(x1.x, w[oo].x, po[1][oo]);
-                po[0][oo] = fmaf(x0.y, w[oo].y, po[0][oo]);
-                po[1][oo] = fmaf(x1.y, w[oo].y, po[1][oo]);
-                po[0][oo] = fmaf(x0.z, w[oo].z, po[0][oo]);
-                po[1][oo] = fmaf(x1.z, w[oo].z, po[1][oo]);
-                po[0][oo] = fmaf(x0.w, w[oo].w, po[0][oo]);
-                po[1][oo] = fmaf(x1.w, w[oo].w, po[1][oo]);
+                for (int oo = 0; oo < OUTS; ++oo) {
+                  po[0][oo] = fmaf(x0.x, w[oo].x, po[0][oo]);
+                  po[1][oo] = fmaf(x1.x, w[oo].x, po[1][oo]);
+                  po[0][oo] = fmaf(x0.y, w[oo].y, po[0][oo]);
+                  po[1][oo] = fmaf(x1.y, w[oo].y, po[1][oo]);
+                  po[0][oo] = fmaf(x0.z, w[oo].z, po[0][oo]);
+                  po[1][oo] = fmaf(x1.z, w[oo].z, po[1][oo]);
+                  po[0][oo] = fmaf(x0.w, w[oo].w, po[0][oo]);
+                  po[1][oo] = fmaf(x1.w, w[oo].w, po[1][oo]);
+                }
               }
-            }
-            if (tid == 0) trace_ev(p, g * 4 + 2, 2);
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+              for (int q = 0; q < 2; ++q)
 #pragma unroll
-              for (int oo = 0; oo < OUTS; ++oo) {
-                float x = po[h][oo];
-                x += __shfl_xor_sync(0xffffffffu, x, 1);
-                x += __shfl_xor_sync(0xffffffffu, x, 2);
-                po[h][oo] = x;
+                for (int oo = 0; oo < OUTS; ++oo) {
+                  float x = po[q][oo];
+                  x += __shfl_xor_sync(0xffffffffu, x, 1);
+                  x += __shfl_xor_sync(0xffffffffu, x, 2);
+                  po[q][oo] = x;
+                }
+              if (kq == 0) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                  for (int o4 = 0; o4 < OUTS / 4; ++o4)
+                    sts128(smem_u32(sm.ptile) + ((row0 + 2 * rp + q) * kPad + og * OUTS + 4 * o4) * 4,
+                           make_float4(po[q][4 * o4], po[q][4 * o4 + 1], po[q][4 * o4 + 2], po[q][4 * o4 + 3]));
               }
-            if (kq == 0) {
-#pragma unroll
-              for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int o4 = 0; o4 < OUTS / 4; ++o4)
-                  sts128(smem_u32(sm.ptile) + ((2 * rp + h) * kPad + og * OUTS + 4 * o4) * 4,
-                         make_float4(po[h][4 * o4], po[h][4 * o4 + 1], po[h][4 * o4 + 2], po[h][4 * o4 + 3]));
+              fence_proxy_async_smem();
             }
+            bar_epi<ET>();
           }
-          if (tid == 0) trace_ev(p, g * 4 + 2, 3);
-          fence_proxy_async_smem();
-          if (tid == 0) trace_ev(p, g * 4 + 2, 4);
-          bar_epi();
           if (tid == 0) trace_ev(p, g * 4 + 3, 14);
+          // ---- exchange the partial sums: one bulk store + flag per CTA, then every CTA sums the team's tiles in a
+          //      fixed order straight from L2 ----
           const uint32_t pexp = p.epoch + 1 + part_w[pb];
           if (warp == 0) {
             if (lane == 0) {
@@ -617,65 +634,64 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
             }
             __syncwarp();
             for (int c = lane; c < NT; c += 32) wait_flag(pflag + pb * NT + c, pexp, p.status, launch_id);
-            __syncwarp();
-            fence_proxy_async_smem();
-            if (lane == 0) {
-              // all partial tiles of the team in one copy: [NT][RT][16] fp32, over the (now dead) transposed tile
-              mbar_arrive_expect_tx(&sm.pland_full, NT * RT * kPad * 4);
-              bulk_g2s(sm.outbox, part_slot + (size_t)pb * NT * RT * kPad, NT * RT * kPad * 4, &sm.pland_full);
-            }
+            __threadfence();  // acquire for the plain loads below
           }
-          mbar_wait(&sm.pland_full, pxchg & 1);
+          bar_epi<ET>();
           if (tid == 0) trace_ev(p, g * 4 + 3, 12);
-          {
-            const uint32_t land = smem_u32(sm.outbox);
-            for (int i = tid; i < RT * 4; i += kEpiThreads) {
-              const int r = i >> 2, o4 = i & 3;
-              float4 s = lds128(sp_a + (kSmLastB + 4 * o4) * 4);
-              for (int c = 0; c < NT; ++c) {  // fixed order: bitwise identical replicas
-                const float4 x = lds128(land + ((c * RT + r) * kPad + 4 * o4) * 4);
-                s.x += x.x;
-                s.y += x.y;
-                s.z += x.z;
-                s.w += x.w;
+          for (int i = tid; i < RT * 4; i += ET) {
+            const int r = i >> 2, o4 = i & 3;
+            float4 acc = lds128(sp_a + (kSmLastB + 4 * o4) * 4);
+            const float* src = part_slot + ((size_t)pb * NT * RT + r) * kPad + 4 * o4;
+            float4 x[8];
+            for (int c0 = 0; c0 < NT; c0 += 8) {  // fixed order: bitwise identical replicas
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                x[c] = c0 + c < NT ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)(c0 + c) * RT * kPad))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                acc.x += x[c].x;
+                acc.y += x[c].y;
+                acc.z += x[c].z;
+                acc.w += x[c].w;
               }
-              sts128(smem_u32(&sm.a[r][4 * o4]), s);
             }
+            sts128(smem_u32(&sm.a[r][4 * o4]), acc);
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.small_empty[sb]);
           ++part_w[pb];
           ++pxchg;
-          bar_epi();
-          for (int i = tid; i < RT * tg_len; i += kEpiThreads) {
+          bar_epi<ET>();
+          for (int i = tid; i < RT * tg_len; i += ET) {
             const int r = i / tg_len, j = i % tg_len;
             const float sc = p.clamp_scale * atanf(sm.a[r][j]);
             const float tr = sm.a[r][tg_len + j];
             sm.u[r][tg_off + j] = (sm.u[r][tg_off + j] - tr) * expf(-sc);
           }
-          bar_epi();
+          bar_epi<ET>();
           if (tid == 0) trace_ev(p, g * 4 + 3, 13);
         }
         {
-          constexpr int kPer = (RT * kPad + kEpiThreads - 1) / kEpiThreads;
+          constexpr int kPer = (RT * kPad + ET - 1) / ET;
           float tmp[kPer];
 #pragma unroll
           for (int c = 0; c < kPer; ++c) {
-            const int i = tid + c * kEpiThreads;
+            const int i = tid + c * ET;
             tmp[c] = i < RT * p.W ? sm.u[i / p.W][p.perm_inv[blk * kPad + i % p.W]] : 0.f;
           }
-          bar_epi();
+          bar_epi<ET>();
 #pragma unroll
           for (int c = 0; c < kPer; ++c) {
-            const int i = tid + c * kEpiThreads;
+            const int i = tid + c * ET;
             if (i < RT * p.W) sm.u[i / p.W][i % p.W] = tmp[c];
           }
-          bar_epi();
+          bar_epi<ET>();
         }
       }
 
       if (t == 0) {
-        for (int i = tid; i < RT * p.out_cols; i += kEpiThreads) {
+        for (int i = tid; i < RT * p.out_cols; i += ET) {
           const int r = i / p.out_cols, j = i % p.out_cols;
           const int row = rg * RT + r;
           if (row >= p.batch) continue;
@@ -691,13 +707,13 @@ __global__ void __launch_bounds__(kThreadsU, 1) flow_inverse_umma_kernel(const F
           p.out[(size_t)row * p.out_ld + j] = o;
         }
       }
-      bar_epi();
+      bar_epi<ET>();
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarpU) {
+  if (warp == C::kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(C::kTmemCols) : "memory");
   }
 }

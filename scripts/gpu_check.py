@@ -156,6 +156,7 @@ if __name__ == "__main__":
         hp.dim_latent_space = 7
         solver, _, _ = flow_checks("panda", hp, "panda", 512, blockwise=True)
         flow_checks("panda", hp, "panda", 1000)
+        flow_checks("panda", hp, "panda", 2500)
     if "time" in which:
         for b in (64, 512, 2048, 8192):
             timing(solver, b, iters=30)
