@@ -177,6 +177,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16x1"])
+    ap.add_argument("--mode", default="approx", choices=["approx", "exact"],
+                    help="approx = generate_ik_solutions (headline); exact = generate_exact_ik_solutions (flow + LM refinement)")
     args = ap.parse_args()
     warmup = max(args.warmup, 3)
 
@@ -184,7 +186,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {
-        "workload": f"{args.model}, batch={args.batch} per GPU, approximate solve (generate_ik_solutions), synthetic seeded weights",
+        "workload": f"{args.model}, batch={args.batch} per GPU, "
+        + ("approximate solve (generate_ik_solutions)" if args.mode == "approx" else "generate_exact_ik_solutions (flow + LM refine, repeat_counts (1,3,10), 1 mm / 0.01 rad)")
+        + ", synthetic seeded weights",
         "batch_per_gpu": args.batch,
         "global_batch": args.batch * world,
         "parallelism": f"batch-sharded x{world}, weights replicated, one all-gather of the joint angles per step" if world > 1 else "single GPU",
@@ -234,7 +238,10 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB of L2
 
     def step_resident():
-        local = solver.generate_ik_solutions(poses, latent=latent)
+        if args.mode == "exact":  # BASELINE.json configs[2]: thresholds of scripts/benchmark_generate_exact_solutions.py:18-19
+            local, _valid = solver.generate_exact_ik_solutions(poses, pos_error_threshold=1e-3, rot_error_threshold=1e-2)
+        else:
+            local = solver.generate_ik_solutions(poses, latent=latent)
         return all_gather_rows(local, B * world) if world > 1 else local
 
     for _ in range(warmup):
@@ -278,7 +285,10 @@ def main():
 
     def step_e2e():
         y = poses_host.to(dev, non_blocking=True)
-        sol = solver.generate_ik_solutions(y)  # draws its own latent on the device, like the reference
+        if args.mode == "exact":
+            sol, _valid = solver.generate_exact_ik_solutions(y, pos_error_threshold=1e-3, rot_error_threshold=1e-2)
+        else:
+            sol = solver.generate_ik_solutions(y)  # draws its own latent on the device, like the reference
         if world > 1:
             sol = all_gather_rows(sol, B * world)[rank * B : (rank + 1) * B]
         out_host.copy_(sol, non_blocking=True)

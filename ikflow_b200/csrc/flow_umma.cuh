@@ -50,15 +50,16 @@ struct Cfg {
   static constexpr int kEpiRows = RT / kGroups;
   static constexpr int kEpiWarps = 4 * kGroups;
   static constexpr int kEpiThreads = 32 * kEpiWarps;
-  static constexpr int kLoaderWarp0 = kEpiWarps;  // first loader warp
-  static constexpr int kMmaWarp = kEpiWarps + kLoaderWarps;
-  static constexpr int kStorerWarp = kMmaWarp + 1;
-  static constexpr int kThreads = (kStorerWarp + 1) * 32;
   static constexpr int kStages = RT == 32 ? 4 : 2;
   // loader warp w owns the ring stages s with s % kLoaders == w: its waits on a stage's barriers are then strictly in
   // order (a waiter may lag an mbarrier by at most one phase)
   static constexpr int kLoaders = kStages < kLoaderWarps ? kStages : kLoaderWarps;
   static_assert(kStages % kLoaders == 0, "every stage needs exactly one owner");
+  static constexpr int kLoaderWarp0 = kEpiWarps;  // first loader warp
+  static constexpr int kMmaWarp = kEpiWarps + kLoaders;
+  static constexpr int kStorerWarp = kMmaWarp + 1;
+  // registers are granted per 4 warps: 10 or 12 warps leave 170 registers per thread, 14 would leave 128
+  static constexpr int kThreads = (kStorerWarp + 1) * 32;
   static constexpr int kHalfPlane = kEpiRows * kKC * 2;  // one bf16 plane of one k-chunk for the rows of one group
   static constexpr int kOutbox = 4 * kHalfPlane;         // [k-chunk 2][head|tail][kEpiRows][64 k] = kEpiRows*512 bytes
   static constexpr int kTmemCols = 2 * RT <= 32 ? 32 : (2 * RT <= 64 ? 64 : (2 * RT <= 128 ? 128 : 256));  // D[:, 0:2RT]
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
   const int my_rgs = (p.n_rowgroups - slot + p.slots - 1) / p.slots;
   const int total_steps = my_rgs * steps_per_rg;
 
-  if (warp >= C::kLoaderWarp0 && warp < C::kLoaderWarp0 + kLoaderWarps) {
+  if (warp >= C::kLoaderWarp0 && warp < C::kLoaderWarp0 + C::kLoaders) {
     // ===== loaders: bulk-TMA producers.  k-chunk number pos = ring_pos + i (counted over the whole launch) goes to ring
     // stage pos % kStages and is loaded by loader warp pos % kLoaders; warp 0 also prefetches the small parameters and
     // pulls the next layer's weights into L2.  Chunks are consumed in the fixed order kc = (2t + i) % KCH, so the
@@ -288,7 +289,6 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
         }
         uint32_t ready = gave_up ? 0xffffffffu : 0u;  // bit c: producer c has published (warp-uniform)
         for (int i = (lw + C::kLoaders - (int)(ring_pos % C::kLoaders)) % C::kLoaders; i < KCH; i += C::kLoaders) {
-          if (lw >= C::kLoaders) break;
           const uint32_t pos = ring_pos + i;
           const int st = pos % kStages;
           const uint32_t use = pos / kStages;
@@ -567,54 +567,60 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
             if (h == hh) {
               // thread = (k quarter kq, row pair rp, output group og): 2 rows x OUTS outputs over 32 of the 128
               // features, then a 4-lane shuffle reduction over the k quarters
-              constexpr int OUTS = ER / 4;  // 8 (ER = 32) or 16 (ER = 64)
-              const int kq = f & 3, rp = (f >> 2) % (ER / 2), og = f / (2 * ER);
-              float po[2][OUTS];
-#pragma unroll
-              for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int oo = 0; oo < OUTS; ++oo) po[q][oo] = 0.f;
+              constexpr int OUTS = 8;                 // outputs per pass
+              constexpr int PASSES = ER / 32;          // ER = 32: threads split the 16 outputs two ways, one pass;
+                                                       // ER = 64: every thread owns all 16 outputs, two passes
+              const int kq = f & 3, rp = (f >> 2) % (ER / 2), og0 = (f / (2 * ER)) * PASSES;
               const uint32_t vrow = outbox_a + (2 * rp) * kFTU * 4;
-              const uint32_t wrow = sp_a + (kSmLastW + og * OUTS * kFTU) * 4;
-              const int osw = (og * OUTS) >> 2;  // (o >> 2) = osw + (oo >> 2)
-#pragma unroll 2
-              for (int jj = 0; jj < 8; ++jj) {
-                const int slot_ = (kq << 3) | ((jj ^ kq ^ (rp << 2)) & 7);  // both rows of the pair share (row >> 1)
-                // all loads of the step first, then the FMAs (see the first layer)
-                float4 w[OUTS];
-                const float4 x0 = lds128(vrow + (slot_ << 4));
-                const float4 x1 = lds128(vrow + kFTU * 4 + (slot_ << 4));
 #pragma unroll
-                for (int oo = 0; oo < OUTS; ++oo)
-                  w[oo] = lds128(wrow + (oo * kFTU + (((kq << 3) | ((jj ^ kq ^ (osw + (oo >> 2))) & 7)) << 2)) * 4);
-#pragma unroll
-                for (int oo = 0; oo < OUTS; ++oo) {
-                  po[0][oo] = fmaf(x0.x, w[oo].x, po[0][oo]);
-                  po[1][oo] = fmaf(x1.x, w[oo].x, po[1][oo]);
-                  po[0][oo] = fmaf(x0.y, w[oo].y, po[0][oo]);
-                  po[1][oo] = fmaf(x1.y, w[oo].y, po[1][oo]);
-                  po[0][oo] = fmaf(x0.z, w[oo].z, po[0][oo]);
-                  po[1][oo] = fmaf(x1.z, w[oo].z, po[1][oo]);
-                  po[0][oo] = fmaf(x0.w, w[oo].w, po[0][oo]);
-                  po[1][oo] = fmaf(x1.w, w[oo].w, po[1][oo]);
-                }
-              }
-#pragma unroll
-              for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int oo = 0; oo < OUTS; ++oo) {
-                  float x = po[q][oo];
-                  x += __shfl_xor_sync(0xffffffffu, x, 1);
-                  x += __shfl_xor_sync(0xffffffffu, x, 2);
-                  po[q][oo] = x;
-                }
-              if (kq == 0) {
+              for (int ps = 0; ps < PASSES; ++ps) {
+                const int og = og0 + ps;  // outputs og*8 .. og*8+7
+                float po[2][OUTS];
 #pragma unroll
                 for (int q = 0; q < 2; ++q)
 #pragma unroll
-                  for (int o4 = 0; o4 < OUTS / 4; ++o4)
-                    sts128(smem_u32(sm.ptile) + ((row0 + 2 * rp + q) * kPad + og * OUTS + 4 * o4) * 4,
-                           make_float4(po[q][4 * o4], po[q][4 * o4 + 1], po[q][4 * o4 + 2], po[q][4 * o4 + 3]));
+                  for (int oo = 0; oo < OUTS; ++oo) po[q][oo] = 0.f;
+                const uint32_t wrow = sp_a + (kSmLastW + og * OUTS * kFTU) * 4;
+                const int osw = (og * OUTS) >> 2;  // (o >> 2) = osw + (oo >> 2)
+#pragma unroll 2
+                for (int jj = 0; jj < 8; ++jj) {
+                  const int slot_ = (kq << 3) | ((jj ^ kq ^ (rp << 2)) & 7);  // both rows of the pair share (row >> 1)
+                  // all loads of the step first, then the FMAs (see the first layer)
+                  float4 w[OUTS];
+                  const float4 x0 = lds128(vrow + (slot_ << 4));
+                  const float4 x1 = lds128(vrow + kFTU * 4 + (slot_ << 4));
+#pragma unroll
+                  for (int oo = 0; oo < OUTS; ++oo)
+                    w[oo] = lds128(wrow + (oo * kFTU + (((kq << 3) | ((jj ^ kq ^ (osw + (oo >> 2))) & 7)) << 2)) * 4);
+#pragma unroll
+                  for (int oo = 0; oo < OUTS; ++oo) {
+                    po[0][oo] = fmaf(x0.x, w[oo].x, po[0][oo]);
+                    po[1][oo] = fmaf(x1.x, w[oo].x, po[1][oo]);
+                    po[0][oo] = fmaf(x0.y, w[oo].y, po[0][oo]);
+                    po[1][oo] = fmaf(x1.y, w[oo].y, po[1][oo]);
+                    po[0][oo] = fmaf(x0.z, w[oo].z, po[0][oo]);
+                    po[1][oo] = fmaf(x1.z, w[oo].z, po[1][oo]);
+                    po[0][oo] = fmaf(x0.w, w[oo].w, po[0][oo]);
+                    po[1][oo] = fmaf(x1.w, w[oo].w, po[1][oo]);
+                  }
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                  for (int oo = 0; oo < OUTS; ++oo) {
+                    float x = po[q][oo];
+                    x += __shfl_xor_sync(0xffffffffu, x, 1);
+                    x += __shfl_xor_sync(0xffffffffu, x, 2);
+                    po[q][oo] = x;
+                  }
+                if (kq == 0) {
+#pragma unroll
+                  for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int o4 = 0; o4 < OUTS / 4; ++o4)
+                      sts128(smem_u32(sm.ptile) + ((row0 + 2 * rp + q) * kPad + og * OUTS + 4 * o4) * 4,
+                             make_float4(po[q][4 * o4], po[q][4 * o4 + 1], po[q][4 * o4 + 2], po[q][4 * o4 + 3]));
+                }
               }
               fence_proxy_async_smem();
             }

@@ -229,3 +229,21 @@ def test_repeated_calls_are_bitwise_identical_under_load(engine, monkeypatch):
         differing += int(not torch.equal(model.inverse(latent, cond), ref))
     assert differing == 0
     assert model.status() == 0
+
+
+@pytest.mark.parametrize("engine,rt,batch", [("mma", "32", 200), ("mma", "64", 200), ("umma", "32", 700), ("umma", "64", 100), ("umma", "128", 300)])
+def test_every_engine_and_row_group_size(engine, rt, batch, monkeypatch):
+    """The two engines (mma.sync tiles / tcgen05 + TMEM) and every row-group size, forced explicitly (the library picks
+    them from the batch size otherwise), against the oracle."""
+    monkeypatch.setenv("IKFLOW_B200_ENGINE", engine)
+    monkeypatch.setenv("IKFLOW_B200_RT", rt)
+    hp = IkflowModelParameters()
+    hp.nb_nodes, hp.dim_latent_space = 12, 7
+    robot = ikflow_b200.Panda()
+    sd = make_synthetic_state_dict(hp, robot.actuated_joints_limits, seed=0)
+    model = ikflow_b200.glow_cNF_model(hp, robot, 8, 7)
+    model.load_state_dict(sd)
+    latent, poses, cond = _inputs(batch, 7)
+    out = model.inverse(latent.to(DEV), cond.to(DEV))
+    assert (out.cpu() - _oracle(sd, hp, latent, cond)).abs().max() < TOL
+    assert model.status() == 0
