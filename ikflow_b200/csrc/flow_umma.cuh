@@ -45,23 +45,21 @@ struct Cfg {
   static constexpr int kAChunk = 2 * kAPlane;        // head + tail
   static constexpr int kStage = kWChunkU + kAChunk;  // 40 KB (RT=32) / 48 KB (RT=64)
   // Epilogue threads: 128 per group (thread = TMEM lane = hidden feature); a group drains EPI_ROWS accumulator columns.
-  // RT = 128 uses two groups (rows 0-63 and 64-127) that share the outbox one after the other.
+  // RT = 128 uses two groups (rows 0-63 and 64-127) that work side by side.
   static constexpr int kGroups = RT > 64 ? 2 : 1;
   static constexpr int kEpiRows = RT / kGroups;
   static constexpr int kEpiWarps = 4 * kGroups;
   static constexpr int kEpiThreads = 32 * kEpiWarps;
-  static constexpr int kStages = RT == 32 ? 4 : 2;
+  static constexpr int kStages = RT == 32 ? 4 : (RT == 64 ? 3 : 2);
   // loader warp w owns the ring stages s with s % kLoaders == w: its waits on a stage's barriers are then strictly in
   // order (a waiter may lag an mbarrier by at most one phase)
   static constexpr int kLoaders = kStages < kLoaderWarps ? kStages : kLoaderWarps;
   static_assert(kStages % kLoaders == 0, "every stage needs exactly one owner");
   static constexpr int kLoaderWarp0 = kEpiWarps;  // first loader warp
   static constexpr int kMmaWarp = kEpiWarps + kLoaders;
-  static constexpr int kStorerWarp = kMmaWarp + 1;
-  // registers are granted per 4 warps: 10 or 12 warps leave 170 registers per thread, 14 would leave 128
-  static constexpr int kThreads = (kStorerWarp + 1) * 32;
-  static constexpr int kHalfPlane = kEpiRows * kKC * 2;  // one bf16 plane of one k-chunk for the rows of one group
-  static constexpr int kOutbox = 4 * kHalfPlane;         // [k-chunk 2][head|tail][kEpiRows][64 k] = kEpiRows*512 bytes
+  // registers are granted per 4 warps: up to 12 warps leave 170 registers per thread, 13+ would leave 128
+  static constexpr int kThreads = (kMmaWarp + 1) * 32;
+  static constexpr int kVtBytes = 32 * kFTU * 4;         // fp32 [32 rows][128 features] of one group: last-layer operand
   static constexpr int kTmemCols = 2 * RT <= 32 ? 32 : (2 * RT <= 64 ? 64 : (2 * RT <= 128 ? 128 : 256));  // D[:, 0:2RT]
   static_assert(kStage % 1024 == 0, "stages must keep the 1024-byte alignment of the swizzle atoms");
 };
@@ -70,9 +68,8 @@ template <int RT>
 struct __align__(1024) Smem {
   using C = Cfg<RT>;
   uint8_t ring[C::kStages][C::kStage];  // [weights head|tail][activations head|tail]
-  // publish staging of one epilogue group (two swizzled bf16 k-chunks)  |  its fp32 activations [kEpiRows][128] for the
-  // last layer
-  uint8_t outbox[C::kOutbox];
+  // per epilogue group: fp32 activations [32 rows][128 features] for the last layer (float4 slots swizzled)
+  uint8_t vt[C::kGroups][C::kVtBytes];
   float ptile[RT * kPad];  // this CTA's partial sums of the last layer
   float small[2][kSmallFloatsU];
   float u[RT][kPad];  // flow state
@@ -81,7 +78,7 @@ struct __align__(1024) Smem {
   float a[RT][kPad];
   uint64_t full[C::kStages], empty[C::kStages];
   uint64_t small_full[2], small_empty[2];
-  uint64_t staging_free, dfull, dempty;
+  uint64_t dfull, dempty;
   uint32_t tmem_base;
 };
 
@@ -180,9 +177,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 
 template <int N>
 __device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
-// one epilogue group (128 threads) + the storer warp: "the outgoing chunk is staged"
-__device__ __forceinline__ void bar_staged_arrive_u() { asm volatile("bar.arrive 2, %0;" ::"n"(128 + 32) : "memory"); }
-__device__ __forceinline__ void bar_staged_sync_u() { asm volatile("bar.sync 2, %0;" ::"n"(128 + 32) : "memory"); }
+// the 128 threads of one epilogue group
+__device__ __forceinline__ void bar_group(int h) { asm volatile("bar.sync %0, 128;" ::"r"(3 + h) : "memory"); }
+__device__ __forceinline__ void stg128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 template <int RT>
 __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel(const FlowParams p) {
@@ -210,7 +209,6 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
       mbar_init(&sm.small_full[b], 1);
       mbar_init(&sm.small_empty[b], C::kEpiWarps);
     }
-    mbar_init(&sm.staging_free, 1);
     mbar_init(&sm.dfull, 1);
     mbar_init(&sm.dempty, C::kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -386,40 +384,6 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
         }
       }
     }
-  } else if (warp == C::kStorerWarp) {
-    // ===== storer: publishes this CTA's 128 features (two k-chunks) to the team, one epilogue group at a time =====
-    // scratch layout of a producer: [k-chunk 2][head|tail][RT rows][64 k]; a group contributes ER rows of each plane,
-    // i.e. four regions of kHalfPlane bytes, stored by four lanes at once
-    uint32_t act_w[2] = {0, 0};
-    uint32_t xchg = 0;
-    for (int g = 0; g < total_steps; ++g) {
-      for (int l = 0; l < p.n_big; ++l) {
-        const int buf = xchg & 1;
-        for (int hh = 0; hh < G; ++hh) {
-          bar_staged_sync_u();  // the group has written + proxy-fenced the outbox
-          if (lane == 0) trace_ev(p, g * 4 + l, 3);
-          if (lane < 4) {
-            uint8_t* dst = act_slot + ((size_t)buf * NT + t) * kAStrideU + (size_t)lane * C::kAPlane + (size_t)hh * C::kHalfPlane;
-            bulk_s2g(dst, sm.outbox + lane * C::kHalfPlane, C::kHalfPlane);
-            bulk_commit();
-            bulk_wait_all();
-          }
-          __syncwarp();
-          if (lane == 0) {
-            trace_ev(p, g * 4 + l, 4);
-            // The release is NOT optional: completion of a bulk store (wait_group) makes its bytes visible to the
-            // issuing thread only.  A relaxed flag store here lets consumers read stale chunks
-            // (scripts/stress_flow.py: 37 of 1500 calls differed); the MEMBAR.GPU of st.release costs ~1 us per exchange.
-            if (hh == G - 1) st_release(aflag + buf * NT + t, p.epoch + 1 + act_w[buf]);
-            trace_ev(p, g * 4 + l, 5);
-            mbar_arrive(&sm.staging_free);
-          }
-          __syncwarp();
-        }
-        ++act_w[buf];
-        ++xchg;
-      }
-    }
   } else {
     // ===== epilogue / SIMT warps: thread (f, h) owns hidden feature 128 t + f (TMEM lane f) for the rows of group h =====
     const int f = tid & 127;
@@ -430,10 +394,12 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
     const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t part_w[2] = {0, 0};
     uint32_t pxchg = 0;
-    uint32_t pubs = 0;     // uses of the outbox handed to the storer so far (all groups count all uses)
-    uint32_t layers = 0;   // hidden layers drained so far
+    uint32_t act_w[2] = {0, 0};  // publishes so far into each activation scratch buffer
+    uint32_t axchg = 0;          // activation exchanges so far
+    uint32_t layers = 0;         // hidden layers drained so far
     const bool x3 = p.precision == IKF_PRECISION_BF16X3;
-    const uint32_t outbox_a = smem_u32(sm.outbox);
+    const uint32_t vt_a = smem_u32(sm.vt[h]);
+    const int j8 = lane & 7;     // publish: row inside an 8-row block after the lane transpose
     const uint32_t xin_a = smem_u32(&sm.a[0][0]);
 
     int g = 0;
@@ -527,105 +493,125 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
               if (tid == 0) trace_ev(p, g * 4 + l - 1, 9);
             }
             if (l < p.n_big) {
-              // ---- publish: head/tail split into the swizzled planes of the outbox, one group after the other ----
+              // ---- publish straight from the registers: bf16 head/tail split, 8x8 transpose across the 8 lanes that hold
+              //      8 consecutive features (so that every lane owns one 16-byte chunk = 8 features of one row), two
+              //      16-byte global stores per lane and 8-row block into the producer's slot of the scratch ring
+              //      [k-chunk 2][head|tail][RT rows][64 k, swizzled]; then ONE release flag per CTA ----
+              const int buf = axchg & 1;
+              uint8_t* dst = act_slot + ((size_t)buf * NT + t) * kAStrideU + (size_t)sub * C::kAChunk;
+              const int kf8 = kf & ~7;
 #pragma unroll
-              for (int hh = 0; hh < G; ++hh) {
-                if (h == hh) {
-                  if (pubs > 0) mbar_wait(&sm.staging_free, (pubs - 1) & 1);
-                  const uint32_t ob = outbox_a + sub * 2 * C::kHalfPlane;
+              for (int r0 = 0; r0 < ER; r0 += 8) {
+                uint32_t wd[8];
 #pragma unroll
-                  for (int r = 0; r < ER; ++r) {
-                    const __nv_bfloat16 hi = __float2bfloat16_rn(v[r]);
-                    const __nv_bfloat16 lo = __float2bfloat16_rn(v[r] - __bfloat162float(hi));
-                    const uint32_t off = tile_off_bytes(r, kf);  // (row0 + r) & 7 == r & 7: ER is a multiple of 8
-                    sts16(ob + off, __bfloat16_as_ushort(hi));
-                    sts16(ob + C::kHalfPlane + off, __bfloat16_as_ushort(lo));
-                  }
-                  fence_proxy_async_smem();
-                  bar_staged_arrive_u();
+                for (int i = 0; i < 8; ++i) {
+                  const __nv_bfloat16 hi = __float2bfloat16_rn(v[r0 + i]);
+                  const __nv_bfloat16 lo = __float2bfloat16_rn(v[r0 + i] - __bfloat162float(hi));
+                  wd[i] = pack_bf16(hi, lo);  // head in the low half, tail in the high half
                 }
-                ++pubs;
+                // before: lane j8 (feature kf8 + j8) holds rows r0..r0+7; after: lane j8 holds row r0 + j8, features kf8..kf8+7
+#pragma unroll
+                for (int st = 4; st >= 1; st >>= 1) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    if ((i & st) == 0) {
+                      const bool up = (j8 & st) != 0;
+                      const uint32_t send = up ? wd[i] : wd[i + st];
+                      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, st);
+                      if (up) wd[i] = recv; else wd[i + st] = recv;
+                    }
+                  }
+                }
+                const uint32_t off = tile_off_bytes(row0 + r0 + j8, kf8);
+                stg128(dst + off, __byte_perm(wd[0], wd[1], 0x5410), __byte_perm(wd[2], wd[3], 0x5410),
+                       __byte_perm(wd[4], wd[5], 0x5410), __byte_perm(wd[6], wd[7], 0x5410));
+                stg128(dst + C::kAPlane + off, __byte_perm(wd[0], wd[1], 0x7632), __byte_perm(wd[2], wd[3], 0x7632),
+                       __byte_perm(wd[4], wd[5], 0x7632), __byte_perm(wd[6], wd[7], 0x7632));
               }
+              bar_epi<ET>();
+              // st.release is cumulative over the stores the barrier ordered before it.  It is NOT optional: a relaxed
+              // flag store lets consumers read stale chunks (scripts/stress_flow.py); its MEMBAR.GPU costs ~1 us.
+              if (tid == 0) {
+                trace_ev(p, g * 4 + l, 4);
+                st_release(aflag + buf * NT + t, p.epoch + 1 + act_w[buf]);
+                trace_ev(p, g * 4 + l, 5);
+              }
+              ++act_w[buf];
+              ++axchg;
               if (tid == 0) trace_ev(p, g * 4 + l, 10);
             }
           }
 
-          // ---- last layer: fp32, through a transposed copy of the activations (one group at a time) ----
+          // ---- last layer: fp32, through a transposed copy of the activations; every group works on its own rows, 32 at a
+          //      time ----
           if (tid == 0) trace_ev(p, g * 4 + 3, 11);
           const int pb = pxchg & 1;
-          if (pubs > 0) mbar_wait(&sm.staging_free, (pubs - 1) & 1);  // the storer is done with the outbox
+          {
+            // thread = (k quarter kq, row pair rp, output group og): 2 rows x 8 outputs over 32 of the 128 features,
+            // then a 4-lane shuffle reduction over the k quarters
+            constexpr int OUTS = 8;
+            const int kq = f & 3, rp = (f >> 2) & 15, og = f >> 6;
+            const uint32_t vrow = vt_a + (2 * rp) * kFTU * 4;
+            const uint32_t wrow = sp_a + (kSmLastW + og * OUTS * kFTU) * 4;
+            const int osw = (og * OUTS) >> 2;  // (o >> 2) = osw + (oo >> 2)
 #pragma unroll
-          for (int hh = 0; hh < G; ++hh) {
-            // [ER][128] fp32; float4 slot j4 of row r sits at (j4 & ~7) | ((j4 ^ (j4 >> 3) ^ ((r >> 1) << 2)) & 7): the 8
-            // lanes of a quarter warp of the reader below (4 k-quarters x 2 row pairs) then hit 8 different bank groups
-            if (h == hh) {
+            for (int ps = 0; ps < ER / 32; ++ps) {
+              // [32][128] fp32; float4 slot j4 of row r sits at (j4 & ~7) | ((j4 ^ (j4 >> 3) ^ ((r >> 1) << 2)) & 7): the 8
+              // lanes of a quarter warp of the reader (4 k-quarters x 2 row pairs) then hit 8 different bank groups
 #pragma unroll
-              for (int r = 0; r < ER; ++r)
-                sts32(outbox_a + (r * kFTU + (((((f >> 2) & ~7) | (((f >> 2) ^ (f >> 5) ^ ((r >> 1) << 2)) & 7)) << 2) | (f & 3))) * 4, v[r]);
-            }
-            bar_epi<ET>();
-            if (h == hh) {
-              // thread = (k quarter kq, row pair rp, output group og): 2 rows x OUTS outputs over 32 of the 128
-              // features, then a 4-lane shuffle reduction over the k quarters
-              constexpr int OUTS = 8;                 // outputs per pass
-              constexpr int PASSES = ER / 32;          // ER = 32: threads split the 16 outputs two ways, one pass;
-                                                       // ER = 64: every thread owns all 16 outputs, two passes
-              const int kq = f & 3, rp = (f >> 2) % (ER / 2), og0 = (f / (2 * ER)) * PASSES;
-              const uint32_t vrow = outbox_a + (2 * rp) * kFTU * 4;
+              for (int r = 0; r < 32; ++r)
+                sts32(vt_a + (r * kFTU + (((((f >> 2) & ~7) | (((f >> 2) ^ (f >> 5) ^ ((r >> 1) << 2)) & 7)) << 2) | (f & 3))) * 4,
+                      v[ps * 32 + r]);
+              bar_group(h);
+              float po[2][OUTS];
 #pragma unroll
-              for (int ps = 0; ps < PASSES; ++ps) {
-                const int og = og0 + ps;  // outputs og*8 .. og*8+7
-                float po[2][OUTS];
+              for (int q = 0; q < 2; ++q)
 #pragma unroll
-                for (int q = 0; q < 2; ++q)
-#pragma unroll
-                  for (int oo = 0; oo < OUTS; ++oo) po[q][oo] = 0.f;
-                const uint32_t wrow = sp_a + (kSmLastW + og * OUTS * kFTU) * 4;
-                const int osw = (og * OUTS) >> 2;  // (o >> 2) = osw + (oo >> 2)
+                for (int oo = 0; oo < OUTS; ++oo) po[q][oo] = 0.f;
 #pragma unroll 2
-                for (int jj = 0; jj < 8; ++jj) {
-                  const int slot_ = (kq << 3) | ((jj ^ kq ^ (rp << 2)) & 7);  // both rows of the pair share (row >> 1)
-                  // all loads of the step first, then the FMAs (see the first layer)
-                  float4 w[OUTS];
-                  const float4 x0 = lds128(vrow + (slot_ << 4));
-                  const float4 x1 = lds128(vrow + kFTU * 4 + (slot_ << 4));
+              for (int jj = 0; jj < 8; ++jj) {
+                const int slot_ = (kq << 3) | ((jj ^ kq ^ (rp << 2)) & 7);  // both rows of the pair share (row >> 1)
+                // all loads of the step first, then the FMAs (see the first layer)
+                float4 w[OUTS];
+                const float4 x0 = lds128(vrow + (slot_ << 4));
+                const float4 x1 = lds128(vrow + kFTU * 4 + (slot_ << 4));
 #pragma unroll
-                  for (int oo = 0; oo < OUTS; ++oo)
-                    w[oo] = lds128(wrow + (oo * kFTU + (((kq << 3) | ((jj ^ kq ^ (osw + (oo >> 2))) & 7)) << 2)) * 4);
+                for (int oo = 0; oo < OUTS; ++oo)
+                  w[oo] = lds128(wrow + (oo * kFTU + (((kq << 3) | ((jj ^ kq ^ (osw + (oo >> 2))) & 7)) << 2)) * 4);
 #pragma unroll
-                  for (int oo = 0; oo < OUTS; ++oo) {
-                    po[0][oo] = fmaf(x0.x, w[oo].x, po[0][oo]);
-                    po[1][oo] = fmaf(x1.x, w[oo].x, po[1][oo]);
-                    po[0][oo] = fmaf(x0.y, w[oo].y, po[0][oo]);
-                    po[1][oo] = fmaf(x1.y, w[oo].y, po[1][oo]);
-                    po[0][oo] = fmaf(x0.z, w[oo].z, po[0][oo]);
-                    po[1][oo] = fmaf(x1.z, w[oo].z, po[1][oo]);
-                    po[0][oo] = fmaf(x0.w, w[oo].w, po[0][oo]);
-                    po[1][oo] = fmaf(x1.w, w[oo].w, po[1][oo]);
-                  }
-                }
-#pragma unroll
-                for (int q = 0; q < 2; ++q)
-#pragma unroll
-                  for (int oo = 0; oo < OUTS; ++oo) {
-                    float x = po[q][oo];
-                    x += __shfl_xor_sync(0xffffffffu, x, 1);
-                    x += __shfl_xor_sync(0xffffffffu, x, 2);
-                    po[q][oo] = x;
-                  }
-                if (kq == 0) {
-#pragma unroll
-                  for (int q = 0; q < 2; ++q)
-#pragma unroll
-                    for (int o4 = 0; o4 < OUTS / 4; ++o4)
-                      sts128(smem_u32(sm.ptile) + ((row0 + 2 * rp + q) * kPad + og * OUTS + 4 * o4) * 4,
-                             make_float4(po[q][4 * o4], po[q][4 * o4 + 1], po[q][4 * o4 + 2], po[q][4 * o4 + 3]));
+                for (int oo = 0; oo < OUTS; ++oo) {
+                  po[0][oo] = fmaf(x0.x, w[oo].x, po[0][oo]);
+                  po[1][oo] = fmaf(x1.x, w[oo].x, po[1][oo]);
+                  po[0][oo] = fmaf(x0.y, w[oo].y, po[0][oo]);
+                  po[1][oo] = fmaf(x1.y, w[oo].y, po[1][oo]);
+                  po[0][oo] = fmaf(x0.z, w[oo].z, po[0][oo]);
+                  po[1][oo] = fmaf(x1.z, w[oo].z, po[1][oo]);
+                  po[0][oo] = fmaf(x0.w, w[oo].w, po[0][oo]);
+                  po[1][oo] = fmaf(x1.w, w[oo].w, po[1][oo]);
                 }
               }
-              fence_proxy_async_smem();
+#pragma unroll
+              for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int oo = 0; oo < OUTS; ++oo) {
+                  float x = po[q][oo];
+                  x += __shfl_xor_sync(0xffffffffu, x, 1);
+                  x += __shfl_xor_sync(0xffffffffu, x, 2);
+                  po[q][oo] = x;
+                }
+              if (kq == 0) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                  for (int o4 = 0; o4 < OUTS / 4; ++o4)
+                    sts128(smem_u32(sm.ptile) + ((row0 + ps * 32 + 2 * rp + q) * kPad + og * OUTS + 4 * o4) * 4,
+                           make_float4(po[q][4 * o4], po[q][4 * o4 + 1], po[q][4 * o4 + 2], po[q][4 * o4 + 3]));
+              }
+              if (ps + 1 < ER / 32) bar_group(h);  // the tile is free for the next 32 rows
             }
-            bar_epi<ET>();
           }
+          fence_proxy_async_smem();
+          bar_epi<ET>();
           if (tid == 0) trace_ev(p, g * 4 + 3, 14);
           // ---- exchange the partial sums: one bulk store + flag per CTA, then every CTA sums the team's tiles in a
           //      fixed order straight from L2 ----
