@@ -336,9 +336,9 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"], "traffic": 205_156_352 + 3_525_120 if args.model == "panda__full__lp191_5.25m" and B == 512 else None,
+                "frac": achieved / peaks["bf16_tflops"], "traffic": 204_991_232 + 4_015_616 if args.model == "panda__full__lp191_5.25m" and B == 512 else None,
                 "peak_source": peaks["source"] + ", burst bf16",
-                "kernel": "ikf::umma::flow_inverse_umma_kernel<32>" if B <= 576 else "ikf::umma::flow_inverse_umma_kernel<64>", "kernel_ms": kernel_ms,
+                "kernel": "ikf::umma::flow_inverse_umma_kernel<%d>" % (32 if B <= 576 else 64 if B <= 1152 else 128), "kernel_ms": kernel_ms,
                 "algorithmic_flops_per_launch": fl * B,
                 "hbm": {"algorithmic_bytes_per_launch": wbytes + B * 84, "achieved_gbs": (wbytes + B * 84) / (kernel_ms * 1e-3) / 1e9,
                         "peak_gbs": peaks["hbm_gbs"], "frac": (wbytes + B * 84) / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
