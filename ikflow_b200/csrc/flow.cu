@@ -385,6 +385,7 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   p.epoch = flow->epoch;
   p.trace = flow->trace;
   p.trace_layers = flow->trace_layers;
+  if (const char* env = std::getenv("IKFLOW_B200_DEBUG")) p.debug = std::atoi(env);
   // every flag of this launch stays below epoch + 1 + (row groups per slot) * (subnets) * (exchanges per subnet)
   const uint32_t rg_per_slot = (uint32_t)((p.n_rowgroups + p.slots - 1) / p.slots);
   flow->epoch += rg_per_slot * 2u * (uint32_t)(block_first - block_last + 1) * (uint32_t)(flow->n_big + 1) + 2u;

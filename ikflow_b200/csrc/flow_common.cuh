@@ -54,8 +54,9 @@ struct FlowParams {
   uint32_t* part_flag;  // [slot][2][NT]
   uint32_t* status;     // [0] status bits, [1] id of the launch that aborted
   uint32_t epoch;       // sequence numbers of this launch start at epoch + 1
-  unsigned long long* trace;  // debug: [cta < NT][layer][16] globaltimer stamps of team 0 (NULL = off)
+  unsigned long long* trace;  // debug: [cta < NT][layer][96] globaltimer stamps of team 0 (NULL = off)
   int trace_layers;
+  int debug;  // timing experiments only (IKFLOW_B200_DEBUG): results are garbage when non-zero
   const float* in;
   const float* cond;
   float* out;
@@ -192,11 +193,18 @@ __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t expecte
   }
 }
 
+constexpr int kTraceEvents = 96;  // stamps per (CTA, layer): 0-15 phase events; per k-chunk i: 16+i landed (MMA warp), 32+i stage free
+                                  // (loader), 48+i copies issued, 64+i expect_tx done, 80+i weight copy issued
+// per-chunk stamps (events 16..63) use the SM clock: cheap to read, only compared inside one CTA
+__device__ __forceinline__ void trace_clk(const FlowParams& p, int layer, int ev) {
+  if (p.trace != nullptr && (p.debug & 4) && blockIdx.x < p.NT && layer < p.trace_layers)  // IKFLOW_B200_DEBUG=4: they perturb
+    p.trace[((size_t)blockIdx.x * p.trace_layers + layer) * kTraceEvents + ev] = (unsigned long long)clock64();
+}
 __device__ __forceinline__ void trace_ev(const FlowParams& p, int layer, int ev) {
   if (p.trace != nullptr && blockIdx.x < p.NT && layer < p.trace_layers) {
     unsigned long long tns;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
-    p.trace[((size_t)blockIdx.x * p.trace_layers + layer) * 16 + ev] = tns;
+    p.trace[((size_t)blockIdx.x * p.trace_layers + layer) * kTraceEvents + ev] = tns;
   }
 }
 

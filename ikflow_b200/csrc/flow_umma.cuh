@@ -157,6 +157,12 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// one lane of the (converged) warp; ptxas recognises the pattern and emits the guarded code without per-thread loops
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
@@ -256,6 +262,20 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
       }
       __syncwarp();
     };
+    // Hidden-layer weights into L2, two layers ahead of their use.  A weight slice is read by the CTAs t of ALL teams at
+    // about the same time, so the teams share the work: team `slot` prefetches the k-chunks k = slot (mod slots) of its
+    // CTAs' slices.  (Every CTA prefetching its whole slice -- 512 KB per layer through the SM's bulk-copy engine, next
+    // to 640 KB of real loads -- delayed the loads: DRAM-sourced weights cost 4.5 us per subnet against L2-resident ones.)
+    auto prefetch_layer = [&](int q) {
+      const int g2 = q / p.n_big, l2 = q % p.n_big;
+      if (g2 >= total_steps) return;
+      const int in_rg2 = g2 % steps_per_rg;
+      const int n2 = 2 * (p.block_first - in_rg2 / 2) + (in_rg2 & 1);
+      const uint8_t* wnext =
+          reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n2 * p.n_big + l2) * NT + t) * KCH * kWChunkU;
+      for (int k = lane; k < KCH; k += 32)
+        if (k % p.slots == slot) bulk_prefetch_l2(wnext + (size_t)k * kWChunkU, kWChunkU);
+    };
     if (lw == 0) prefetch_small(0);
     bool gave_up = false;
     for (int g = 0; g < total_steps; ++g) {
@@ -268,33 +288,24 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
             reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n * p.n_big + l) * NT + t) * KCH * kWChunkU;
         const uint8_t* abase = act_slot + (size_t)buf * NT * kAStrideU;
         const uint32_t* my_flag = aflag + buf * NT + (lane < NT ? lane : 0);
-        if (lw == 0) {
-          // next hidden layer's weight slice (KCH x 32 KB) into L2, one layer ahead of its use
-          int n2 = n, l2 = l + 1;
-          if (l2 == p.n_big) {
-            l2 = 0;
-            n2 = -1;
-            if (g + 1 < total_steps) {
-              const int in_rg2 = (g + 1) % steps_per_rg;
-              n2 = 2 * (p.block_first - in_rg2 / 2) + (in_rg2 & 1);
-            }
-          }
-          if (n2 >= 0) {
-            const uint8_t* wnext =
-                reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n2 * p.n_big + l2) * NT + t) * KCH * kWChunkU;
-            for (int k = lane; k < KCH; k += 32) bulk_prefetch_l2(wnext + (size_t)k * kWChunkU, kWChunkU);
-          }
-        }
+        bool prefetched = lw != C::kLoaders - 1;  // the last loader warp pulls weights into L2, see prefetch_layer
         uint32_t ready = gave_up ? 0xffffffffu : 0u;  // bit c: producer c has published (warp-uniform)
         for (int i = (lw + C::kLoaders - (int)(ring_pos % C::kLoaders)) % C::kLoaders; i < KCH; i += C::kLoaders) {
           const uint32_t pos = ring_pos + i;
           const int st = pos % kStages;
           const uint32_t use = pos / kStages;
-          if (use > 0) mbar_wait_relaxed(&sm.empty[st], (use - 1) & 1);
+          // everything that does not depend on the stage being free is computed before the wait
           const int kc = (2 * t + i) % KCH;
           const int c = kc >> 1;
           const void* wsrc = wbase + (size_t)kc * kWChunkU;
           const void* asrc = abase + (size_t)c * kAStrideU + (size_t)(kc & 1) * C::kAChunk;
+          // lane 0 copies the weights, lane 1 the activations: copies of one thread are processed one after the other,
+          // copies of different threads side by side (scripts/ubench/ingest2.cu)
+          const void* my_src = lane == 0 ? wsrc : asrc;
+          uint8_t* my_dst = sm.ring[st] + (lane == 0 ? 0 : kWChunkU);
+          const uint32_t my_bytes = lane == 0 ? (uint32_t)kWChunkU : (uint32_t)C::kAChunk;
+          if (use > 0) mbar_wait_relaxed(&sm.empty[st], (use - 1) & 1);
+          if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 32 + i);
           // one look at the flags: if the producer is already done, weights and activations go out together
           if (!((ready >> c) & 1u)) {
             bool ok = false;
@@ -302,11 +313,19 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
             ready |= __ballot_sync(0xffffffffu, ok);
           }
           const bool a_now = (ready >> c) & 1u;
-          if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], C::kStage);
+          if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 64 + i);
+          // No ordering is needed between lane 0's expect_tx and lane 1's copy: the phase cannot complete before the
+          // (single) pending arrival, which is the expect_tx itself, whatever the transient sign of the tx-count.
+          if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], (p.debug & 1 ? 0 : C::kAChunk) + (p.debug & 2 ? 0 : kWChunkU));
+          if (lane < (a_now ? 2 : 1) && !((p.debug >> (1 - lane)) & 1)) bulk_g2s(my_dst, my_src, my_bytes, &sm.full[st]);
           __syncwarp();
-          if (lane == 0) bulk_g2s(sm.ring[st], wsrc, kWChunkU, &sm.full[st]);
-          if (lane == 1 && a_now) bulk_g2s(sm.ring[st] + kWChunkU, asrc, C::kAChunk, &sm.full[st]);
-          __syncwarp();
+          if (!prefetched) {  // after this warp's first copies of the layer are on their way
+            prefetched = true;
+            const int q = g * p.n_big + l;
+            if (q == 0) prefetch_layer(1);
+            prefetch_layer(q + 2);
+          }
+          if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 80 + i);
           if (lane == 0 && i == 0) trace_ev(p, g * 4 + l, 0);
           if (!a_now) {
             uint32_t spins = 0;
@@ -337,12 +356,13 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
                 }
               }
             }
-            if (lane == 0) bulk_g2s(sm.ring[st] + kWChunkU, asrc, C::kAChunk, &sm.full[st]);
+            if (lane == 0 && !(p.debug & 1)) bulk_g2s(sm.ring[st] + kWChunkU, asrc, C::kAChunk, &sm.full[st]);
             __syncwarp();
           }
           if (lane == 0) {
             if (i == 0) trace_ev(p, g * 4 + l, 1);
             if (i == KCH - 1) trace_ev(p, g * 4 + l, 2);
+            if (p.trace != nullptr && i < 16) trace_clk(p, g * 4 + l, 48 + i);
           }
         }
         if (lw == 0 && l == 0) prefetch_small(g + 1);
@@ -353,8 +373,11 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
       if (lw == 0 && p.n_big == 0) prefetch_small(g + 1);
     }
   } else if (warp == C::kMmaWarp) {
-    // ===== MMA issuer: one thread drives the tensor core =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp runs the loop (warp-uniform control flow), one elected lane drives the tensor
+    // core.  With `if (lane == 0)` around the loop ptxas wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY
+    // loop ("once per active thread"); behind elect.sync the UTCHMMAs are emitted back to back: 840 -> 560 cycles per
+    // k-chunk for the issuing thread (scripts/ubench/umma_loop.cu), which is what paces the hidden layers. =====
+    {
       constexpr uint32_t idesc = make_idesc(kFTU, RT);       // N = RT
       constexpr uint32_t idesc2 = make_idesc(kFTU, 2 * RT);  // N = 2 RT: activation head and tail stacked
       uint32_t ring_pos = 0;
@@ -362,24 +385,55 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
       const bool x3 = p.precision == IKF_PRECISION_BF16X3;
       const uint64_t d_wh0 = make_desc(smem_u32(sm.ring[0])), d_wl0 = make_desc(smem_u32(sm.ring[0]) + kWPlaneU);
       const uint64_t d_a0 = make_desc(smem_u32(sm.ring[0]) + kWChunkU);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const bool static_ring = (KCH % kStages) == 0;  // every layer then starts at ring stage 0
       for (int g = 0; g < total_steps; ++g) {
         for (int l = 0; l < p.n_big; ++l) {
           if (layers > 0) mbar_wait(&sm.dempty, (layers - 1) & 1);  // the epilogue has drained the accumulator
           tc_fence_after();
-          for (int i = 0; i < KCH; ++i) {
-            const int s = ring_pos % kStages;
-            mbar_wait(&sm.full[s], (ring_pos / kStages) & 1);
-            tc_fence_after();
-            const uint64_t soff = (uint64_t)(s * (C::kStage >> 4));  // stage offset in the 16-byte address field
-            if (x3)
-              mma_chunk_x3(tmem, idesc2, idesc, d_wh0 + soff, d_wl0 + soff, d_a0 + soff, i != 0);
-            else
-              mma_chunk_x1(tmem, idesc, d_wh0 + soff, d_a0 + soff, i != 0);
-            mma_commit(&sm.empty[s]);  // the stage is free once these MMAs have read it
-            ++ring_pos;
+          if (static_ring) {
+            // stage index = i % kStages is a compile-time constant inside the unrolled group: the 3 descriptors of every
+            // stage stay in uniform registers (428 instead of 459 cycles of issue per chunk, scripts/ubench/umma_loop.cu)
+            for (int i0 = 0; i0 < KCH; i0 += kStages) {
+              const uint32_t par = (ring_pos / kStages) & 1;
+#pragma unroll
+              for (int s = 0; s < kStages; ++s) {
+                mbar_wait(&sm.full[s], par);
+                tc_fence_after();
+                if (p.trace != nullptr && lane == 0 && i0 + s < 16) trace_clk(p, g * 4 + l, 16 + i0 + s);
+                constexpr uint64_t kStageOff = (uint64_t)(C::kStage >> 4);  // stage offset in the 16-byte address field
+                if (elect_one()) {
+                  if (x3)
+                    mma_chunk_x3(tmem_u, idesc2, idesc, d_wh0 + s * kStageOff, d_wl0 + s * kStageOff, d_a0 + s * kStageOff, (i0 + s) != 0);
+                  else
+                    mma_chunk_x1(tmem_u, idesc, d_wh0 + s * kStageOff, d_a0 + s * kStageOff, (i0 + s) != 0);
+                  mma_commit(&sm.empty[s]);  // the stage is free once these MMAs have read it
+                }
+                __syncwarp();
+              }
+              ring_pos += kStages;
+            }
+          } else {
+            for (int i = 0; i < KCH; ++i) {
+              const int s = ring_pos % kStages;
+              mbar_wait(&sm.full[s], (ring_pos / kStages) & 1);
+              tc_fence_after();
+              if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 16 + i);
+              const uint64_t soff = (uint64_t)(s * (C::kStage >> 4));
+              if (elect_one()) {
+                if (x3)
+                  mma_chunk_x3(tmem_u, idesc2, idesc, d_wh0 + soff, d_wl0 + soff, d_a0 + soff, i != 0);
+                else
+                  mma_chunk_x1(tmem_u, idesc, d_wh0 + soff, d_a0 + soff, i != 0);
+                mma_commit(&sm.empty[s]);
+              }
+              __syncwarp();
+              ++ring_pos;
+            }
           }
-          mma_commit(&sm.dfull);  // accumulator complete
-          trace_ev(p, g * 4 + l, 8);
+          if (elect_one()) mma_commit(&sm.dfull);  // accumulator complete
+          __syncwarp();
+          if (lane == 0) trace_ev(p, g * 4 + l, 8);
           ++layers;
         }
       }

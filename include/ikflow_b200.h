@@ -118,8 +118,8 @@ int ikf_flow_status(IkfFlow* flow, void* stream, uint32_t* status_out);
 /* Introspection for benchmarks: bytes of packed weights resident in HBM, CTAs per launch, dynamic smem per CTA. */
 int ikf_flow_info(IkfFlow* flow, size_t* packed_weight_bytes, int* grid_ctas_last, int* smem_bytes);
 
-/* Debug aid: the CTAs of team 0 write %globaltimer stamps [cta][layer][16] (layer = 4*subnet step + layer index) into
- * dev_stamps (device memory, (hidden/64)*n_layers*16 uint64) during the next launches.  n_layers = 0 switches it off. */
+/* Debug aid: the CTAs of team 0 write %globaltimer stamps [cta][layer][96] (layer = 4*subnet step + layer index) into
+ * dev_stamps (device memory, (hidden/64)*n_layers*96 uint64) during the next launches.  n_layers = 0 switches it off. */
 int ikf_flow_debug_trace(IkfFlow* flow, unsigned long long* dev_stamps, int n_layers);
 
 /* ---- kinematics --------------------------------------------------------------------------------------------------

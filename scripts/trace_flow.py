@@ -1,4 +1,7 @@
-"""Developer aid: per-layer timeline of CTA 0 of the flow kernel (globaltimer stamps)."""
+"""Developer aid: per-layer timeline of team 0 of the flow kernel (globaltimer stamps), after a long warm-up.
+
+usage: python scripts/trace_flow.py [batch] [subnets traced] [nb_nodes]
+"""
 import os
 import sys
 
@@ -10,40 +13,78 @@ from ikflow_b200 import _lib
 from ikflow_b200.model import IkflowModelParameters, make_synthetic_state_dict
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+nsub = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 hp = IkflowModelParameters()
 hp.dim_latent_space = 7
+if len(sys.argv) > 3:
+    hp.nb_nodes = int(sys.argv[3])
 robot = ikflow_b200.get_robot("panda")
 solver = ikflow_b200.IKFlowSolver(hp, robot)
+if os.environ.get("TRACE_PRECISION"):
+    solver.nn_model.precision = os.environ["TRACE_PRECISION"]
 solver.load_state_dict_from_dict(make_synthetic_state_dict(hp, robot.actuated_joints_limits, seed=0))
 g = torch.Generator().manual_seed(0)
 latent = torch.randn(batch, 7, generator=g).cuda()
 poses = robot.forward_kinematics(robot.sample_joint_angles(batch, generator=g))
-for _ in range(3):
+for _ in range(300):
     solver.generate_ik_solutions(poses, latent=latent)
 torch.cuda.synchronize()
-nl = 24
+EV = 96
+nl = 4 * nsub
 NT = 16
-stamps = torch.zeros(NT * nl * 16, dtype=torch.int64, device="cuda")
+stamps = torch.zeros(NT * nl * EV, dtype=torch.int64, device="cuda")
 h = solver.nn_model._handle(torch.device("cuda", 0))
 _lib.check(_lib.lib().ikf_flow_debug_trace(h, stamps.data_ptr(), nl), "trace")
 solver.generate_ik_solutions(poses, latent=latent)
 torch.cuda.synchronize()
 _lib.lib().ikf_flow_debug_trace(h, None, 0)
-sa = stamps.cpu().view(NT, nl, 16)
-t0 = int(sa[sa > 0].min())
-s = sa[0]
-names = ["W0 issue", "A first", "A last", "st:sync", "st:done", "st:flag", "c:start", "c:full0", "c:mma end", "c:v ready", "c:staged", "p:start", "p:flags", "p:coupled", "p:dot", "p:myflag"]
-print("layer " + " ".join(f"{n:>10s}" for n in names))
-for i in range(8):
-    row = [(int(v) - t0) / 1000.0 if v > 0 else float("nan") for v in s[i, :16]]
-    print(f"{i:5d} " + " ".join(f"{v:10.2f}" for v in row))
-
-print("per-CTA stamps of selected events (us):")
-for layer, ev, nm in [(1, 7, "full0"), (1, 8, "mma end"), (1, 5, "flag"), (3, 11, "p:start"), (3, 12, "p:flags"), (4, 10, "L0 staged")]:
-    print(f"layer {layer} {nm:>10s}: " + " ".join(f"{(int(v) - t0) / 1000.0:7.2f}" for v in sa[:, layer, ev]))
+sa = stamps.cpu().view(NT, nl, EV)
+t0 = int(sa[:, :, :16][sa[:, :, :16] > 0].min())
+T = 8
 
 
+def us(v):
+    return (int(v) - t0) / 1000.0 if v > 0 else float("nan")
 
-print("dot phase detail (row 4g+2): vt stored, bar passed, dot loop done, shuffles+ptile done, fence done")
-for i in (2, 6, 10):
-    print(i, " ".join(f"{(int(v) - t0) / 1000.0:8.2f}" for v in sa[0, i, :5]))
+
+names = ["W0 issue", "A first", "A last", "-", "st:done", "st:flag", "c:start", "c:full0", "c:mma end", "c:v ready", "c:staged", "p:start", "p:flags", "p:coupled", "p:dot", "p:myflag"]
+print("CTA 0:")
+print("layer " + " ".join(f"{n:>9s}" for n in names))
+for i in range(nl):
+    print(f"{i:5d} " + " ".join(f"{us(v):9.2f}" for v in sa[0, i, :16]))
+
+print("\nper-CTA stamps (us), subnets 1..:")
+for sub in range(1, nsub):
+    b = 4 * sub
+    for layer, ev, nm in [(b, 10, "L0 staged"), (b, 5, "L0 flag"), (b, 1, "H0 A first"), (b, 2, "H0 A last"), (b, 8, "H0 mma end"), (b + 1, 10, "H0 staged"),
+                          (b + 1, 1, "H1 A first"), (b + 1, 2, "H1 A last"), (b + 1, 8, "H1 mma end"), (b + 3, 11, "p:start"), (b + 3, 14, "p:dot"), (b + 3, 15, "p:myflag"),
+                          (b + 3, 12, "p:flags"), (b + 3, 13, "p:coupled")]:
+        print(f"sub {sub} {nm:>10s}: " + " ".join(f"{us(v):7.2f}" for v in sa[:T, layer, ev]))
+    print()
+
+print("per k-chunk SM-clock stamps (cycles, relative to the layer's first landed chunk): MMA warp saw the stage full / loader saw the stage free / loader issued the copies")
+for cta in (0, 3):
+    for layer in (4, 5, 8, 9):
+        if layer < nl:
+            base = int(sa[cta, layer, 16])
+            print(f"cta {cta} layer {layer}:\n   landed " + " ".join(f"{int(v) - base:6d}" for v in sa[cta, layer, 16:32]))
+            print("   free   " + " ".join(f"{int(v) - base:6d}" for v in sa[cta, layer, 32:48]))
+            print("   expect " + " ".join(f"{int(v) - base:6d}" for v in sa[cta, layer, 64:80]))
+            print("   W sent " + " ".join(f"{int(v) - base:6d}" for v in sa[cta, layer, 80:96]))
+            print("   issued " + " ".join(f"{int(v) - base:6d}" for v in sa[cta, layer, 48:64]))
+
+# phase summary, averaged over subnets 1.. and the CTAs of the team
+import statistics as st
+rows = []
+for sub in range(1, nsub - 1):
+    b = 4 * sub
+    for c in range(T):
+        e = lambda l, v: int(sa[c, l, v])
+        prev_coupled = int(sa[c, b - 1, 13])
+        nxt_coupled = e(b + 3, 13)
+        rows.append(dict(total=nxt_coupled - prev_coupled, first=e(b, 10) - prev_coupled, x1=e(b, 1) - e(b, 10), h0=e(b, 8) - e(b, 1), pub=e(b + 1, 10) - e(b, 8),
+                         x2=e(b + 1, 1) - e(b + 1, 10), h1=e(b + 1, 8) - e(b + 1, 1), epi=e(b + 3, 11) - e(b + 1, 8), dot=e(b + 3, 14) - e(b + 3, 11),
+                         myflag=e(b + 3, 15) - e(b + 3, 14), wait=e(b + 3, 12) - e(b + 3, 15), couple=e(b + 3, 13) - e(b + 3, 12)))
+print("\nphase means over subnets 1..%d x %d CTAs (us):" % (nsub - 2, T))
+for k in rows[0]:
+    print(f"  {k:>7s} {st.mean(r[k] for r in rows) / 1000.0:6.2f}")

@@ -47,7 +47,7 @@ int main() {
   printf("grid,S,D,T,by_warp,P,GB/s per CTA,GB/s total\n");
   int grids[] = {1, 148};
   for (int gi = 0; gi < 2; ++gi) for (int by_warp = 0; by_warp < 2; ++by_warp) {
-    int cfg[][4] = {{16384,2,1,1},{16384,2,2,1},{16384,2,4,1},{16384,1,4,1},{16384,1,6,1},{8192,2,4,1},{8192,1,8,1},{4096,2,8,1},{65536,1,1,1},{65536,2,1,1},{32768,2,2,1},{32768,1,3,1},{16384,2,1,2},{16384,2,1,4},{32768,2,1,4},{65536,2,1,8},{49152,2,1,1},{49152,2,2,1}};
+    int cfg[][4] = {{16384,2,1,1},{16384,2,2,1},{16384,2,4,1},{16384,1,4,1},{16384,1,6,1},{8192,2,4,1},{8192,1,8,1},{4096,2,8,1},{65536,1,1,1},{65536,2,1,1},{32768,2,2,1},{32768,1,3,1},{16384,2,1,2},{16384,2,1,4},{32768,2,1,4},{65536,2,1,8},{49152,2,1,1},{49152,2,2,1},{32768,1,4,1},{32768,1,6,1},{16384,1,8,1},{16384,1,12,1},{8192,1,16,1},{8192,2,12,1},{40960,1,4,1},{40960,1,5,1},{20480,1,8,1},{20480,2,4,1}};
     for (auto& c : cfg) {
       int S = c[0], D = c[1], T = c[2], P = c[3];
       size_t sm = 1024 + (size_t)S * D * T;
