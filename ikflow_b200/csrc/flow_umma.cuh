@@ -273,8 +273,12 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
       const int n2 = 2 * (p.block_first - in_rg2 / 2) + (in_rg2 & 1);
       const uint8_t* wnext =
           reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n2 * p.n_big + l2) * NT + t) * KCH * kWChunkU;
-      for (int k = lane; k < KCH; k += 32)
+      // ... plus, whatever the team, the first bytes of the chunks this CTA loads first (kc = 2t .. 2t+3): the address
+      // translation for the CTA's new 512 KB slice is then warm when the layer starts
+      for (int k = lane; k < KCH; k += 32) {
         if (k % p.slots == slot) bulk_prefetch_l2(wnext + (size_t)k * kWChunkU, kWChunkU);
+        else if ((p.debug & 8) && ((k - 2 * t) & (KCH - 1)) < 4) bulk_prefetch_l2(wnext + (size_t)k * kWChunkU, (p.debug & 16) ? kWChunkU : 128);
+      }
     };
     if (lw == 0) prefetch_small(0);
     bool gave_up = false;
@@ -322,8 +326,9 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
           if (!prefetched) {  // after this warp's first copies of the layer are on their way
             prefetched = true;
             const int q = g * p.n_big + l;
-            if (q == 0) prefetch_layer(1);
-            prefetch_layer(q + 2);
+            const int dist = (p.debug & 32) ? 0 : (p.debug & 64) ? 1 : (p.debug & 128) ? 3 : (p.debug & 256) ? 4 : 2;
+            if (q == 0) for (int d = 1; d < dist; ++d) prefetch_layer(d);
+            if (dist > 0) prefetch_layer(q + dist);
           }
           if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 80 + i);
           if (lane == 0 && i == 0) trace_ev(p, g * 4 + l, 0);
@@ -356,7 +361,9 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
                 }
               }
             }
-            if (lane == 0 && !(p.debug & 1)) bulk_g2s(sm.ring[st] + kWChunkU, asrc, C::kAChunk, &sm.full[st]);
+            if (lane == 0 && i == 0) trace_ev(p, g * 4 + l, 3);
+            // lane 1, not lane 0: lane 0's weight copy may still be in flight, and a thread's copies are processed in order
+            if (lane == 1 && !(p.debug & 1)) bulk_g2s(my_dst, my_src, my_bytes, &sm.full[st]);
             __syncwarp();
           }
           if (lane == 0) {

@@ -47,14 +47,15 @@ def us(v):
     return (int(v) - t0) / 1000.0 if v > 0 else float("nan")
 
 
-names = ["W0 issue", "A first", "A last", "-", "st:done", "st:flag", "c:start", "c:full0", "c:mma end", "c:v ready", "c:staged", "p:start", "p:flags", "p:coupled", "p:dot", "p:myflag"]
+names = ["W0 issue", "A first", "A last", "flag seen", "st:done", "st:flag", "c:start", "c:full0", "c:mma end", "c:v ready", "c:staged", "p:start", "p:flags", "p:coupled", "p:dot", "p:myflag"]
 print("CTA 0:")
 print("layer " + " ".join(f"{n:>9s}" for n in names))
 for i in range(nl):
     print(f"{i:5d} " + " ".join(f"{us(v):9.2f}" for v in sa[0, i, :16]))
 
+print("per-subnet duration (coupled -> coupled, CTA 0, us): " + " ".join(f"{(int(sa[0, 4 * s_ + 3, 13]) - int(sa[0, 4 * s_ - 1, 13])) / 1000.0:5.1f}" for s_ in range(1, nsub)))
 print("\nper-CTA stamps (us), subnets 1..:")
-for sub in range(1, nsub):
+for sub in range(1, min(nsub, 6)):
     b = 4 * sub
     for layer, ev, nm in [(b, 10, "L0 staged"), (b, 5, "L0 flag"), (b, 1, "H0 A first"), (b, 2, "H0 A last"), (b, 8, "H0 mma end"), (b + 1, 10, "H0 staged"),
                           (b + 1, 1, "H1 A first"), (b + 1, 2, "H1 A last"), (b + 1, 8, "H1 mma end"), (b + 3, 11, "p:start"), (b + 3, 14, "p:dot"), (b + 3, 15, "p:myflag"),
@@ -64,7 +65,7 @@ for sub in range(1, nsub):
 
 print("per k-chunk SM-clock stamps (cycles, relative to the layer's first landed chunk): MMA warp saw the stage full / loader saw the stage free / loader issued the copies")
 for cta in (0, 3):
-    for layer in (4, 5, 8, 9):
+    for layer in (4, 5, 8, 9) if os.environ.get('IKFLOW_B200_DEBUG') == '4' else ():
         if layer < nl:
             base = int(sa[cta, layer, 16])
             print(f"cta {cta} layer {layer}:\n   landed " + " ".join(f"{int(v) - base:6d}" for v in sa[cta, layer, 16:32]))
