@@ -8,7 +8,8 @@ import ctypes
 import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libikflow_b200.so")
+# IKFLOW_B200_LIB: A/B comparisons of two builds on the same GPU box (developer aid)
+LIB_PATH = os.environ.get("IKFLOW_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libikflow_b200.so")
 
 IKF_OK = 0
 IKF_STATUS_NONFINITE = 1

@@ -270,7 +270,7 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   const size_t off_act = align_up(off_consts + consts.size() * 4);
   const size_t act_bytes = (size_t)slots * 2 * NT * (engine ? umma::kAStrideU : kAChunkStride);
   const size_t off_partial = align_up(off_act + act_bytes);
-  const size_t partial_bytes = (size_t)slots * 2 * NT * (engine ? umma::kRTMaxU : kRTMax) * kPad * 4;
+  const size_t partial_bytes = (size_t)slots * 2 * NT * (engine ? umma::kRTMaxU * umma::kPartRowBytes : kRTMax * kPad * 4);
   const size_t off_flags = align_up(off_partial + partial_bytes);
   const size_t flag_bytes = ((size_t)slots * 2 * NT * 2 + 2) * 4;
   f->blob_bytes = align_up(off_flags + flag_bytes);

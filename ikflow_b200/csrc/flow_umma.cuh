@@ -23,6 +23,12 @@ constexpr int kWPlaneU = kFTU * kKC * 2;        // one bf16 plane of a weight ch
 constexpr int kWChunkU = 2 * kWPlaneU;          // head + tail: 32 KB
 constexpr int kRTMaxU = 128;                          // largest row group of this engine
 constexpr int kAStrideU = 2 * 2 * kRTMaxU * kKC * 2;  // scratch bytes reserved per producer: 2 k-chunks x (head+tail): 64 KB
+// Partial sums of the last layer travel in the "LL" format of NCCL's low-latency protocol: every 16-byte unit holds two
+// values and two copies of the exchange's sequence number, {v0, seq, v1, seq}.  An aligned 8-byte pair is written and
+// read as one piece, so a reader that finds both sequence numbers in place has the values: no flag, no fence, no
+// staging -- the producers store from registers and the consumers poll the data itself.
+constexpr int kPartUnits = kPad / 2;            // 16-byte units per row
+constexpr int kPartRowBytes = kPartUnits * 16;  // 128
 // One bulk copy keeps its issuing thread busy for ~0.3-0.45 us whatever its size; copies issued by different warps run
 // concurrently (scripts/ubench/ingest2.cu).  Four loader warps take the k-chunks round robin so that four copies are
 // always being issued.
@@ -70,7 +76,6 @@ struct __align__(1024) Smem {
   uint8_t ring[C::kStages][C::kStage];  // [weights head|tail][activations head|tail]
   // per epilogue group: fp32 activations [32 rows][128 features] for the last layer (float4 slots swizzled)
   uint8_t vt[C::kGroups][C::kVtBytes];
-  float ptile[RT * kPad];  // this CTA's partial sums of the last layer
   float small[2][kSmallFloatsU];
   float u[RT][kPad];  // flow state
   float cnd[RT][8];
@@ -181,6 +186,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void st_ll(void* p, float v0, float v1, uint32_t seq) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%2};" ::"l"(p), "r"(__float_as_uint(v0)), "r"(seq), "r"(__float_as_uint(v1))
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_ll(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 template <int N>
 __device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 // the 128 threads of one epilogue group
@@ -232,9 +246,8 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
   const uint32_t tmem = sm.tmem_base;
 
   uint8_t* act_slot = p.act + (size_t)slot * 2 * NT * kAStrideU;
-  float* part_slot = p.partial + (size_t)slot * 2 * NT * kRTMaxU * kPad;
+  uint8_t* part_slot = reinterpret_cast<uint8_t*>(p.partial) + (size_t)slot * 2 * NT * kRTMaxU * kPartRowBytes;
   uint32_t* aflag = p.act_flag + (size_t)slot * 2 * NT;
-  uint32_t* pflag = p.part_flag + (size_t)slot * 2 * NT;
 
   const int n_blocks = p.block_first - p.block_last + 1;
   const int steps_per_rg = 2 * n_blocks;
@@ -315,6 +328,13 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
             bool ok = false;
             if (lane < NT && !((ready >> lane) & 1u)) ok = (int32_t)(ld_relaxed(my_flag) - expected) >= 0;
             ready |= __ballot_sync(0xffffffffu, ok);
+          }
+          if ((p.debug & 512) && !((ready >> c) & 1u)) {  // experiment: no weight copy in flight while the epilogue releases
+            while (!((ready >> c) & 1u)) {
+              bool ok = false;
+              if (lane < NT && !((ready >> lane) & 1u)) ok = (int32_t)(ld_relaxed(my_flag) - expected) >= 0;
+              ready |= __ballot_sync(0xffffffffu, ok);
+            }
           }
           const bool a_now = (ready >> c) & 1u;
           if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 64 + i);
@@ -607,6 +627,8 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
           //      time ----
           if (tid == 0) trace_ev(p, g * 4 + 3, 11);
           const int pb = pxchg & 1;
+          const uint32_t pexp = p.epoch + 1 + part_w[pb];  // sequence number of this exchange
+          const int n_units = tg_len;                       // 2 * tg_len outputs, two per 16-byte unit
           {
             // thread = (k quarter kq, row pair rp, output group og): 2 rows x 8 outputs over 32 of the 128 features,
             // then a 4-lane shuffle reduction over the k quarters
@@ -660,57 +682,75 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
                   x += __shfl_xor_sync(0xffffffffu, x, 2);
                   po[q][oo] = x;
                 }
-              if (kq == 0) {
+              // all four lanes of a k-quarter group hold the sums: lane kq publishes outputs og*8 + 2kq, +1 of both rows,
+              // straight from its registers, in the LL format
+              if (og * 4 + kq < n_units) {
 #pragma unroll
-                for (int q = 0; q < 2; ++q)
-#pragma unroll
-                  for (int o4 = 0; o4 < OUTS / 4; ++o4)
-                    sts128(smem_u32(sm.ptile) + ((row0 + ps * 32 + 2 * rp + q) * kPad + og * OUTS + 4 * o4) * 4,
-                           make_float4(po[q][4 * o4], po[q][4 * o4 + 1], po[q][4 * o4 + 2], po[q][4 * o4 + 3]));
+                for (int q = 0; q < 2; ++q) {
+                  const float v0 = kq == 0 ? po[q][0] : kq == 1 ? po[q][2] : kq == 2 ? po[q][4] : po[q][6];
+                  const float v1 = kq == 0 ? po[q][1] : kq == 1 ? po[q][3] : kq == 2 ? po[q][5] : po[q][7];
+                  st_ll(part_slot + (((size_t)pb * NT + t) * RT + row0 + ps * 32 + 2 * rp + q) * kPartRowBytes + (og * 4 + kq) * 16,
+                        v0, v1, pexp);
+                }
               }
               if (ps + 1 < ER / 32) bar_group(h);  // the tile is free for the next 32 rows
             }
           }
-          fence_proxy_async_smem();
-          bar_epi<ET>();
-          if (tid == 0) trace_ev(p, g * 4 + 3, 14);
-          // ---- exchange the partial sums: one bulk store + flag per CTA, then every CTA sums the team's tiles in a
-          //      fixed order straight from L2 ----
-          const uint32_t pexp = p.epoch + 1 + part_w[pb];
-          if (warp == 0) {
-            if (lane == 0) {
-              bulk_s2g(part_slot + ((size_t)pb * NT + t) * RT * kPad, sm.ptile, RT * kPad * 4);
-              bulk_commit();
-              bulk_wait_all();
-              st_release(pflag + pb * NT + t, pexp);  // see the storer
-              trace_ev(p, g * 4 + 3, 15);
-            }
-            __syncwarp();
-            for (int c = lane; c < NT; c += 32) wait_flag(pflag + pb * NT + c, pexp, p.status, launch_id);
-            __threadfence();  // acquire for the plain loads below
+          if (tid == 0) {
+            trace_ev(p, g * 4 + 3, 14);
+            trace_ev(p, g * 4 + 3, 15);
           }
-          bar_epi<ET>();
-          if (tid == 0) trace_ev(p, g * 4 + 3, 12);
+          // ---- sum the team's partial sums in a fixed order (bitwise identical replicas), polling the data itself ----
           for (int i = tid; i < RT * 4; i += ET) {
             const int r = i >> 2, o4 = i & 3;
             float4 acc = lds128(sp_a + (kSmLastB + 4 * o4) * 4);
-            const float* src = part_slot + ((size_t)pb * NT * RT + r) * kPad + 4 * o4;
-            float4 x[8];
-            for (int c0 = 0; c0 < NT; c0 += 8) {  // fixed order: bitwise identical replicas
+            const uint8_t* src = part_slot + ((size_t)pb * NT * RT + r) * kPartRowBytes + (2 * o4) * 16;
+            const bool need0 = 2 * o4 < n_units, need1 = 2 * o4 + 1 < n_units;
+            for (int c0 = 0; c0 < NT; c0 += 8) {
+              uint4 x0[8], x1[8];
+              uint32_t spins = 0;
+              long long t0 = 0;
+              while (true) {
+                bool ok = true;
 #pragma unroll
-              for (int c = 0; c < 8; ++c)
-                x[c] = c0 + c < NT ? __ldcg(reinterpret_cast<const float4*>(src + (size_t)(c0 + c) * RT * kPad))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int c = 0; c < 8; ++c) {
+                  x0[c] = make_uint4(0u, pexp, 0u, pexp);
+                  x1[c] = make_uint4(0u, pexp, 0u, pexp);
+                  if (c0 + c < NT) {
+                    if (need0) x0[c] = ld_ll(src + (size_t)(c0 + c) * RT * kPartRowBytes);
+                    if (need1) x1[c] = ld_ll(src + (size_t)(c0 + c) * RT * kPartRowBytes + 16);
+                  }
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                  ok = ok && x0[c].y == pexp && x0[c].w == pexp && x1[c].y == pexp && x1[c].w == pexp;
+                if (ok) break;
+                // bounded: a lost producer must surface as IKF_STATUS_SYNC_TIMEOUT, not as a hung GPU
+                ++spins;
+                if (spins == 64) t0 = clock64();
+                if (spins > 64) {
+                  __nanosleep(20);
+                  if ((spins & 255u) == 0) {
+                    if (ld_relaxed(p.status + 1) == launch_id) break;
+                    if (clock64() - t0 > 2500000000LL) {
+                      atomicOr(p.status, IKF_STATUS_SYNC_TIMEOUT);
+                      atomicExch(p.status + 1, launch_id);
+                      break;
+                    }
+                  }
+                }
+              }
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
-                acc.x += x[c].x;
-                acc.y += x[c].y;
-                acc.z += x[c].z;
-                acc.w += x[c].w;
+                acc.x += __uint_as_float(x0[c].x);
+                acc.y += __uint_as_float(x0[c].z);
+                acc.z += __uint_as_float(x1[c].x);
+                acc.w += __uint_as_float(x1[c].z);
               }
             }
             sts128(smem_u32(&sm.a[r][4 * o4]), acc);
           }
+          if (tid == 0) trace_ev(p, g * 4 + 3, 12);
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.small_empty[sb]);
           ++part_w[pb];

@@ -85,7 +85,26 @@ for sub in range(1, nsub - 1):
         nxt_coupled = e(b + 3, 13)
         rows.append(dict(total=nxt_coupled - prev_coupled, first=e(b, 10) - prev_coupled, x1=e(b, 1) - e(b, 10), h0=e(b, 8) - e(b, 1), pub=e(b + 1, 10) - e(b, 8),
                          x2=e(b + 1, 1) - e(b + 1, 10), h1=e(b + 1, 8) - e(b + 1, 1), epi=e(b + 3, 11) - e(b + 1, 8), dot=e(b + 3, 14) - e(b + 3, 11),
-                         myflag=e(b + 3, 15) - e(b + 3, 14), wait=e(b + 3, 12) - e(b + 3, 15), couple=e(b + 3, 13) - e(b + 3, 12)))
+                         myflag=e(b + 3, 15) - e(b + 3, 14), rel0=e(b, 5) - e(b, 4), rel1=e(b + 1, 5) - e(b + 1, 4), wait=e(b + 3, 12) - e(b + 3, 15), couple=e(b + 3, 13) - e(b + 3, 12)))
 print("\nphase means over subnets 1..%d x %d CTAs (us):" % (nsub - 2, T))
 for k in rows[0]:
     print(f"  {k:>7s} {st.mean(r[k] for r in rows) / 1000.0:6.2f}")
+
+# kernel time with CUDA events: back to back, and with an L2 flush (256 MB fill) before every call as bench.py does
+def timed(flush_buf, n=100):
+    tot = 0.0
+    for _ in range(n):
+        if flush_buf is not None:
+            flush_buf.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        solver.generate_ik_solutions(poses, latent=latent)
+        b.record()
+        b.synchronize()
+        tot += a.elapsed_time(b)
+    return tot / n * 1000.0
+
+
+fl = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+small_fl = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+print(f"\ncall time (us): back to back {timed(None):.1f}, after a 1 MB fill {timed(small_fl):.1f}, after a 256 MB fill {timed(fl):.1f}")
