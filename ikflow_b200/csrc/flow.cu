@@ -86,7 +86,8 @@ struct IkfFlow {
   void* blob = nullptr;  // one device allocation holding everything below
   size_t blob_bytes = 0, big_w_bytes = 0;
   ikf::FlowParams base;  // pointers + model constants; per-call fields filled at launch
-  size_t smem32 = 0, smem64 = 0, smem128 = 0;
+  size_t smem32 = 0, smem64 = 0, smem128 = 0, smem32j = 0;
+  bool jit = false;  // umma engine, 32-row groups: first layer computed just in time by every CTA (flow_umma.cuh)
   int engine = 0;  // 0 = mma.sync tiles (flow_mma.cuh), 1 = tcgen05 / TMEM (flow_umma.cuh)
   uint32_t epoch = 1;  // doubles as launch id; 0 is "no launch aborted"
   int last_grid = 0;
@@ -241,6 +242,27 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
     }
   }
 
+  // umma engine, just-in-time first layer: per (subnet, 64-feature k-chunk) [16 k][64 f] weights + [64] bias
+  std::vector<float> first_jit;
+  if (engine) {
+    first_jit.assign((size_t)n_sub * KCH * umma::kJitChunkFloats, 0.f);
+    const float* wq = weights;
+    for (int i = 0; i < nb; ++i)
+      for (int sidx = 0; sidx < 2; ++sidx) {
+        const int n = 2 * i + sidx;
+        const int in_dim = (sidx == 0 ? s1 : s2) + desc->dim_cond;
+        const int out_dim = 2 * (sidx == 0 ? s2 : s1);
+        const float* w0 = wq;
+        const float* b0 = wq + (size_t)H * in_dim;
+        for (int f_ = 0; f_ < H; ++f_) {
+          float* blk = first_jit.data() + ((size_t)n * KCH + f_ / kKC) * umma::kJitChunkFloats;
+          for (int k = 0; k < in_dim; ++k) blk[k * kKC + f_ % kKC] = w0[(size_t)f_ * in_dim + k];
+          blk[kPad * kKC + f_ % kKC] = b0[f_];
+        }
+        wq += subnet_weight_count(desc, in_dim, out_dim);
+      }
+  }
+
   std::vector<int> perm(nb * kPad, 0);
   for (int i = 0; i < nb; ++i)
     for (int j = 0; j < W; ++j) {
@@ -265,7 +287,8 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   const int slots = f->slots_max;  // upper bound; refined below from the occupancy
   const size_t off_big = 0;
   const size_t off_small = align_up(off_big + big_elems * 2);
-  const size_t off_perm = align_up(off_small + small_floats * 4);
+  const size_t off_jit = align_up(off_small + small_floats * 4);
+  const size_t off_perm = align_up(off_jit + first_jit.size() * 4);
   const size_t off_consts = align_up(off_perm + perm.size() * 4);
   const size_t off_act = align_up(off_consts + consts.size() * 4);
   const size_t act_bytes = (size_t)slots * 2 * NT * (engine ? umma::kAStrideU : kAChunkStride);
@@ -284,12 +307,18 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   e = cudaMemset(base + off_act, 0, f->blob_bytes - off_act);
   if (e == cudaSuccess && big_elems) e = cudaMemcpy(base + off_big, big.data(), big_elems * 2, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(base + off_small, small.data(), small_floats * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !first_jit.empty())
+    e = cudaMemcpy(base + off_jit, first_jit.data(), first_jit.size() * 4, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(base + off_perm, perm.data(), perm.size() * 4, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(base + off_consts, consts.data(), consts.size() * 4, cudaMemcpyHostToDevice);
   if (engine) {
     f->smem32 = sizeof(umma::Smem<32>) + 1024;
     f->smem64 = sizeof(umma::Smem<64>) + 1024;
     f->smem128 = sizeof(umma::Smem<128>) + 1024;
+    f->smem32j = sizeof(umma::Smem<32, true>) + 1024;
+    // the just-in-time first layer needs every hidden layer to start at ring stage 0
+    f->jit = KCH % umma::Cfg<32, true>::kStages == 0 && f->smem32j <= (size_t)prop.sharedMemPerBlockOptin;
+    if (const char* env = std::getenv("IKFLOW_B200_JIT")) f->jit = f->jit && std::atoi(env) != 0;  // A/B comparisons
   } else {
     f->smem32 = sizeof(FlowSmem<32>) + 1024;
     f->smem64 = sizeof(FlowSmem<64>) + 1024;
@@ -303,6 +332,8 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem64);
   if (e == cudaSuccess && engine)
     e = cudaFuncSetAttribute(umma::flow_inverse_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem128);
+  if (e == cudaSuccess && engine && f->jit)
+    e = cudaFuncSetAttribute(umma::flow_inverse_umma_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem32j);
   if (e == cudaSuccess) {
     // the teams spin on each other's flags, so every CTA of a launch must be resident: size the slot count from
     // what the device really fits
@@ -311,7 +342,10 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, k64, threads64, f->smem64);
     if (e == cudaSuccess && engine)
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ128, umma::flow_inverse_umma_kernel<128>, umma::Cfg<128>::kThreads, f->smem128);
-    const int occ = std::min(std::min(occ32, occ64), occ128);
+    int occ32j = 1;
+    if (e == cudaSuccess && engine && f->jit)
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32j, umma::flow_inverse_umma_kernel<32, true>, umma::Cfg<32, true>::kThreads, f->smem32j);
+    const int occ = std::min(std::min(std::min(occ32, occ64), occ128), occ32j);
     if (e == cudaSuccess && occ < 1) {
       ikf_flow_destroy(f);
       return fail(IKF_EDEVICE, "ikf_flow_create: the flow kernel does not fit on an SM of device %d", device);
@@ -330,6 +364,7 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   p.clamp_scale = (float)((double)desc->rnvp_clamp * 0.636);
   p.big_w = (const __nv_bfloat16*)(base + off_big);
   p.small = (const float*)(base + off_small);
+  p.first_jit = engine ? (const float*)(base + off_jit) : nullptr;
   p.perm_inv = (const int*)(base + off_perm);
   p.m_inv = (const float*)(base + off_consts);
   p.flt_b = p.m_inv + kPad * kPad;
@@ -399,10 +434,12 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   int threads;
   size_t smem;
   if (flow->engine) {
-    fn = rt == 32 ? (const void*)umma::flow_inverse_umma_kernel<32>
-                  : rt == 64 ? (const void*)umma::flow_inverse_umma_kernel<64> : (const void*)umma::flow_inverse_umma_kernel<128>;
+    const bool jit = rt == 32 && flow->jit;
+    fn = jit ? (const void*)umma::flow_inverse_umma_kernel<32, true>
+             : rt == 32 ? (const void*)umma::flow_inverse_umma_kernel<32>
+                        : rt == 64 ? (const void*)umma::flow_inverse_umma_kernel<64> : (const void*)umma::flow_inverse_umma_kernel<128>;
     threads = rt == 32 ? umma::Cfg<32>::kThreads : rt == 64 ? umma::Cfg<64>::kThreads : umma::Cfg<128>::kThreads;
-    smem = rt == 32 ? flow->smem32 : rt == 64 ? flow->smem64 : flow->smem128;
+    smem = jit ? flow->smem32j : rt == 32 ? flow->smem32 : rt == 64 ? flow->smem64 : flow->smem128;
   } else {
     fn = rt == 32 ? (const void*)flow_inverse_kernel<32> : (const void*)flow_inverse_kernel<64>;
     threads = kThreads;

@@ -43,6 +43,7 @@ struct FlowParams {
   float clamp_scale;  // rnvp_clamp * 0.636, rounded to fp32 the way torch rounds the Python scalar
   const __nv_bfloat16* big_w;  // [subnet][n_big][NT t][NT c][head|tail][64 f][64 k] swizzled
   const float* small;          // [subnet][NT t][kSmallFloats]
+  const float* first_jit;      // umma engine: [subnet][KCH c][16 k][64 f] + [64] bias per chunk (just-in-time first layer)
   const int* perm_inv;         // [nb_nodes][kPad]
   const float* m_inv;          // [kPad][kPad]  out_j = sum_i (u_i - b_i) m_inv[i][j]
   const float* flt_b;          // [kPad]

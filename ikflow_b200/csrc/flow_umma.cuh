@@ -13,6 +13,8 @@
 // Requires hidden % 128 == 0 and hidden <= 1024.
 #pragma once
 
+#include <type_traits>
+
 #include "flow_common.cuh"
 
 namespace ikf {
@@ -44,12 +46,26 @@ constexpr int kSmLastB = kSmLastW + kPad * kFTU;
 constexpr int kSmallFloatsU = kSmLastB + kPad;  // 4624
 constexpr int kSmallBytesU = kSmallFloatsU * 4;  // 18496
 static_assert(kSmallBytesU % 16 == 0, "bulk copies move multiples of 16 bytes");
+// "JIT" first layer (RT = 32): every CTA computes the first layer of a subnet for ALL hidden features, one 64-feature
+// k-chunk at a time, straight into the activation slot of the ring stage the tensor core is about to read -- while the
+// previous chunks are being multiplied.  No publish, no fence, no flag, no poll, no activation copy for that layer: one
+// of the three team exchanges of a subnet disappears.  The first-layer weights arrive with the stage:
+//   per (subnet, k-chunk): first_w [16 k][64 f] fp32 | first_b [64]
+constexpr int kJitChunkFloats = kPad * kKC + kKC;  // 1088
+constexpr int kJitChunkBytes = kJitChunkFloats * 4;  // 4352
+static_assert(kJitChunkBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
 
-template <int RT>
+template <int RT, bool JIT = false>
 struct Cfg {
+  static_assert(!JIT || RT == 32, "the just-in-time first layer is written for 32-row groups");
   static constexpr int kAPlane = RT * kKC * 2;       // one bf16 plane of an activation k-chunk [RT][64]
   static constexpr int kAChunk = 2 * kAPlane;        // head + tail
-  static constexpr int kStage = kWChunkU + kAChunk;  // 40 KB (RT=32) / 48 KB (RT=64)
+  static constexpr int kW1Off = kWChunkU + kAChunk;   // JIT: first-layer weights of the chunk's 64 features
+  static constexpr int kStage = JIT ? ((kW1Off + kJitChunkBytes + 1023) / 1024) * 1024 : kW1Off;  // 40 KB (RT=32; JIT 45 KB) / 48 KB (RT=64)
+  // JIT: the small-parameter block is loaded without its first-layer part
+  static constexpr int kSmShift = JIT ? kSmBigB : 0;
+  static constexpr int kSmFloats = kSmallFloatsU - kSmShift;
+  static constexpr uint32_t kFullCount = JIT ? 2 : 1;  // arrivals per phase of a stage's full barrier
   // Epilogue threads: 128 per group (thread = TMEM lane = hidden feature); a group drains EPI_ROWS accumulator columns.
   // RT = 128 uses two groups (rows 0-63 and 64-127) that work side by side.
   static constexpr int kGroups = RT > 64 ? 2 : 1;
@@ -70,18 +86,20 @@ struct Cfg {
   static_assert(kStage % 1024 == 0, "stages must keep the 1024-byte alignment of the swizzle atoms");
 };
 
-template <int RT>
+template <int RT, bool JIT = false>
 struct __align__(1024) Smem {
-  using C = Cfg<RT>;
+  using C = Cfg<RT, JIT>;
   uint8_t ring[C::kStages][C::kStage];  // [weights head|tail][activations head|tail]
   // per epilogue group: fp32 activations [32 rows][128 features] for the last layer (float4 slots swizzled)
   uint8_t vt[C::kGroups][C::kVtBytes];
-  float small[2][kSmallFloatsU];
+  float small[2][C::kSmFloats];
   float u[RT][kPad];  // flow state
   float cnd[RT][8];
   // input of the current subnet [state half | condition | 0] at its start, output of its last layer at its end
   float a[RT][kPad];
   uint64_t full[C::kStages], empty[C::kStages];
+  uint64_t w1full[C::kStages];   // JIT: the first-layer weights of the stage's chunk have landed
+  uint64_t w1empty[C::kStages];  // JIT: ... and have been used (the stage's weight/activation areas may still be busy)
   uint64_t small_full[2], small_empty[2];
   uint64_t dfull, dempty;
   uint32_t tmem_base;
@@ -195,6 +213,23 @@ __device__ __forceinline__ uint4 ld_ll(const void* p) {
   asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ void lds128_2x64(uint32_t a, uint64_t& v0, uint64_t& v1) {
+  asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(v0), "=l"(v1) : "r"(a));
+}
+__device__ __forceinline__ void sts128u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 // the 128 threads of one epilogue group
@@ -203,13 +238,13 @@ __device__ __forceinline__ void stg128(void* p, uint32_t a, uint32_t b, uint32_t
   asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-template <int RT>
-__global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel(const FlowParams p) {
-  using C = Cfg<RT>;
+template <int RT, bool JIT = false>
+__global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_kernel(const FlowParams p) {
+  using C = Cfg<RT, JIT>;
   constexpr int kStages = C::kStages;
   constexpr int G = C::kGroups, ER = C::kEpiRows, ET = C::kEpiThreads;
   extern __shared__ uint8_t smem_raw[];
-  Smem<RT>& sm = *reinterpret_cast<Smem<RT>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Smem<RT, JIT>& sm = *reinterpret_cast<Smem<RT, JIT>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -222,8 +257,10 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.full[s], C::kFullCount);
       mbar_init(&sm.empty[s], 1);
+      mbar_init(&sm.w1full[s], 1);
+      mbar_init(&sm.w1empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sm.small_full[b], 1);
@@ -270,8 +307,8 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
       if (lane == 0) {
         const int in_rg = g % steps_per_rg;
         const int n = 2 * (p.block_first - in_rg / 2) + (in_rg & 1);
-        mbar_arrive_expect_tx(&sm.small_full[b], kSmallBytesU);
-        bulk_g2s(sm.small[b], p.small + ((size_t)n * NT + t) * kSmallFloatsU, kSmallBytesU, &sm.small_full[b]);
+        mbar_arrive_expect_tx(&sm.small_full[b], C::kSmFloats * 4);
+        bulk_g2s(sm.small[b], p.small + ((size_t)n * NT + t) * kSmallFloatsU + C::kSmShift, C::kSmFloats * 4, &sm.small_full[b]);
       }
       __syncwarp();
     };
@@ -306,7 +343,11 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
         const uint8_t* abase = act_slot + (size_t)buf * NT * kAStrideU;
         const uint32_t* my_flag = aflag + buf * NT + (lane < NT ? lane : 0);
         bool prefetched = lw != C::kLoaders - 1;  // the last loader warp pulls weights into L2, see prefetch_layer
-        uint32_t ready = gave_up ? 0xffffffffu : 0u;  // bit c: producer c has published (warp-uniform)
+        // JIT: the activations of the first hidden layer are written into the stage by this CTA's own SIMT warps;
+        // the loader brings the first-layer weights of the chunk's 64 features instead, and nothing is exchanged
+        const bool jit_layer = JIT && l == 0;
+        const uint8_t* w1base = reinterpret_cast<const uint8_t*>(p.first_jit) + (size_t)n * KCH * kJitChunkBytes;
+        uint32_t ready = (gave_up || jit_layer) ? 0xffffffffu : 0u;  // bit c: producer c has published (warp-uniform)
         for (int i = (lw + C::kLoaders - (int)(ring_pos % C::kLoaders)) % C::kLoaders; i < KCH; i += C::kLoaders) {
           const uint32_t pos = ring_pos + i;
           const int st = pos % kStages;
@@ -318,9 +359,21 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
           const void* asrc = abase + (size_t)c * kAStrideU + (size_t)(kc & 1) * C::kAChunk;
           // lane 0 copies the weights, lane 1 the activations: copies of one thread are processed one after the other,
           // copies of different threads side by side (scripts/ubench/ingest2.cu)
-          const void* my_src = lane == 0 ? wsrc : asrc;
-          uint8_t* my_dst = sm.ring[st] + (lane == 0 ? 0 : kWChunkU);
-          const uint32_t my_bytes = lane == 0 ? (uint32_t)kWChunkU : (uint32_t)C::kAChunk;
+          const void* my_src = lane == 0 ? wsrc : (jit_layer ? (const void*)(w1base + (size_t)kc * kJitChunkBytes) : asrc);
+          uint8_t* my_dst = sm.ring[st] + (lane == 0 ? 0 : (jit_layer ? C::kW1Off : kWChunkU));
+          const uint32_t my_bytes = lane == 0 ? (uint32_t)kWChunkU : (jit_layer ? (uint32_t)kJitChunkBytes : (uint32_t)C::kAChunk);
+          uint64_t* my_bar = (jit_layer && lane == 1) ? &sm.w1full[st] : &sm.full[st];
+          if (jit_layer) {
+            // the first-layer weights have their own, earlier, hand-over: their area of the stage is free as soon as the
+            // SIMT warps have used it, a chunk time or more before the tensor core lets go of the rest of the stage
+            const uint32_t w1use = (uint32_t)g * (uint32_t)(KCH / kStages) + (uint32_t)(i / kStages);
+            if (w1use > 0) mbar_wait_relaxed(&sm.w1empty[st], (w1use - 1) & 1);
+            if (lane == 1) {
+              mbar_arrive_expect_tx(&sm.w1full[st], kJitChunkBytes);
+              bulk_g2s(my_dst, my_src, my_bytes, my_bar);
+            }
+            __syncwarp();
+          }
           if (use > 0) mbar_wait_relaxed(&sm.empty[st], (use - 1) & 1);
           if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 32 + i);
           // one look at the flags: if the producer is already done, weights and activations go out together
@@ -340,8 +393,15 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
           if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 64 + i);
           // No ordering is needed between lane 0's expect_tx and lane 1's copy: the phase cannot complete before the
           // (single) pending arrival, which is the expect_tx itself, whatever the transient sign of the tx-count.
-          if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], (p.debug & 1 ? 0 : C::kAChunk) + (p.debug & 2 ? 0 : kWChunkU));
-          if (lane < (a_now ? 2 : 1) && !((p.debug >> (1 - lane)) & 1)) bulk_g2s(my_dst, my_src, my_bytes, &sm.full[st]);
+          if (JIT) {
+            // the full barrier of a stage takes two arrivals per phase: the weights' expect_tx, and the SIMT warps' "the
+            // activations are written" in a JIT layer (a second plain arrival of the loader in the other layers)
+            if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], kWChunkU + (jit_layer ? 0 : C::kAChunk));
+            if (lane == 2 && !jit_layer) mbar_arrive(&sm.full[st]);
+          } else {
+            if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], (p.debug & 1 ? 0 : C::kAChunk) + (p.debug & 2 ? 0 : kWChunkU));
+          }
+          if (lane < ((a_now && !jit_layer) ? 2 : 1) && !((p.debug >> (1 - lane)) & 1)) bulk_g2s(my_dst, my_src, my_bytes, my_bar);
           __syncwarp();
           if (!prefetched) {  // after this warp's first copies of the layer are on their way
             prefetched = true;
@@ -394,8 +454,10 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
         }
         if (lw == 0 && l == 0) prefetch_small(g + 1);
         ring_pos += KCH;
-        ++act_w[buf];
-        ++xchg;
+        if (!jit_layer) {  // a JIT layer is not an exchange
+          ++act_w[buf];
+          ++xchg;
+        }
       }
       if (lw == 0 && p.n_big == 0) prefetch_small(g + 1);
     }
@@ -516,13 +578,89 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
           bar_epi<ET>();
 
           float v[ER];  // activations of feature f for the rows of this group
+          if constexpr (JIT) {
+            // ---- first layer, just in time: thread = (row = lane, warp w -> features 16w .. 16w+15 of every 64-feature
+            //      k-chunk).  The row's input stays in registers, the chunk's weights are broadcast reads from the stage;
+            //      16 consecutive features of one row are two whole 16-byte units of the swizzled operand tile.  Same
+            //      fp32 FMA order as the exchanged version: bitwise identical activations. ----
+            if (tid == 0) trace_ev(p, g * 4, 10);
+            uint64_t xx[kPad];  // the row's inputs, each duplicated into both halves of a 64-bit pair
+#pragma unroll
+            for (int k4 = 0; k4 < kPad; k4 += 4) {
+              const float4 xv = lds128(xin_a + (lane * kPad + k4) * 4);
+              xx[k4] = pack2(xv.x, xv.x), xx[k4 + 1] = pack2(xv.y, xv.y), xx[k4 + 2] = pack2(xv.z, xv.z), xx[k4 + 3] = pack2(xv.w, xv.w);
+            }
+            const uint32_t unit_off[2] = {tile_off_bytes(lane, 16 * warp), tile_off_bytes(lane, 16 * warp + 8)};
+            for (int i = 0; i < KCH; ++i) {
+              const int st = i % kStages;  // every layer starts at ring stage 0 (KCH % kStages == 0, checked at launch)
+              {
+                // two conditions: the chunk's first-layer weights have landed, and the tensor core has let go of the
+                // stage's activation area (previous use of the stage).  Probe both before looking at either result.
+                const uint32_t w1par = ((uint32_t)g * (uint32_t)(KCH / kStages) + (uint32_t)(i / kStages)) & 1u;
+                const uint32_t use = ((uint32_t)g * (uint32_t)p.n_big * (uint32_t)KCH + (uint32_t)i) / kStages;
+                const long long t0 = clock64();
+                while (true) {
+                  const bool ok1 = mbar_try_wait(&sm.w1full[st], w1par);
+                  const bool ok2 = use == 0 || mbar_try_wait(&sm.empty[st], (use - 1) & 1);
+                  if (ok1 && ok2) break;
+                  if (clock64() - t0 > 4000000000LL) __trap();
+                }
+              }
+              const uint32_t stage_a = smem_u32(sm.ring[st]);
+              const uint32_t w1_a = stage_a + C::kW1Off + 16 * warp * 4;
+              // packed fp32 math (fma.rn.f32x2: two IEEE FMAs per instruction, same results as fmaf): 96 instead of 192
+              // issue slots per chunk -- this loop has to keep pace with the tensor core (one chunk per ~570 cycles)
+              uint64_t acc[8];
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) lds128_2x64(w1_a + (kPad * kKC + 4 * j4) * 4, acc[2 * j4], acc[2 * j4 + 1]);
+              // straight-line code (no branch per k: the loads of the next k must be free to move above the FMAs of this
+              // one); inputs and weights are zero-padded, and fma(0, 0, acc) leaves acc as it is
+              auto dot_k = [&](auto kb) {
+#pragma unroll
+                for (int k = 0; k < decltype(kb)::value; ++k) {
+#pragma unroll
+                  for (int j4 = 0; j4 < 4; ++j4) {
+                    uint64_t w01, w23;
+                    lds128_2x64(w1_a + (k * kKC + 4 * j4) * 4, w01, w23);
+                    acc[2 * j4] = ffma2(xx[k], w01, acc[2 * j4]);
+                    acc[2 * j4 + 1] = ffma2(xx[k], w23, acc[2 * j4 + 1]);
+                  }
+                }
+              };
+              if (kin <= 12) dot_k(std::integral_constant<int, 12>{});
+              else dot_k(std::integral_constant<int, kPad>{});
+              uint32_t hi[8], lo[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float a0, a1;
+                unpack2(acc[j], a0, a1);
+                a0 = leaky(a0), a1 = leaky(a1);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);  // .x = a0 (low half), one instruction
+                const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - __uint_as_float(hb << 16), a1 - __uint_as_float(hb & 0xffff0000u));
+                hi[j] = hb;
+                lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+              }
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                sts128u(stage_a + kWChunkU + unit_off[u], hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
+                sts128u(stage_a + kWChunkU + C::kAPlane + unit_off[u], lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
+              }
+              fence_proxy_async_smem();  // generic-proxy writes -> the tensor core's (async proxy) reads
+              bar_epi<ET>();
+              if (tid == 0) {
+                mbar_arrive(&sm.full[st]);
+                mbar_arrive(&sm.w1empty[st]);
+                if (i == 0) trace_ev(p, g * 4, 4);
+              }
+            }
+          } else {
           // ---- first layer: fp32 FMA ----
-          {
-            const float b0 = lds32(sp_a + (kSmFirstB + f) * 4);
+            const float b0 = lds32(sp_a + (kSmFirstB - C::kSmShift + f) * 4);
 #pragma unroll
             for (int r = 0; r < ER; ++r) v[r] = b0;
             for (int k4 = 0; k4 < kin; k4 += 4) {  // the input is zero-padded to 16 columns, the weights too
-              const uint32_t wa = sp_a + (kSmFirstW + k4 * kFTU + f) * 4;
+              const uint32_t wa = sp_a + (kSmFirstW - C::kSmShift + k4 * kFTU + f) * 4;
               const float w0 = lds32(wa), w1 = lds32(wa + kFTU * 4), w2 = lds32(wa + 2 * kFTU * 4), w3 = lds32(wa + 3 * kFTU * 4);
               // every epilogue warp is alone on its scheduler: issue the loads of 8 rows back to back, then the 32 FMAs
               // that consume them, so that the shared-memory latency is paid once per batch
@@ -544,7 +682,7 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
             for (int r = 0; r < ER; ++r) v[r] = leaky(v[r]);
           }
 
-          for (int l = 0; l <= p.n_big; ++l) {
+          for (int l = JIT ? 1 : 0; l <= p.n_big; ++l) {
             if (l > 0) {
               // ---- hidden layer l-1: drain the accumulator ----
               if (tid == 0) trace_ev(p, g * 4 + l - 1, 6);
@@ -568,7 +706,7 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
               __syncwarp();
               if (lane == 0) mbar_arrive(&sm.dempty);
               ++layers;
-              const float bb = lds32(sp_a + (kSmBigB + (l - 1) * kFTU + f) * 4);
+              const float bb = lds32(sp_a + (kSmBigB - C::kSmShift + (l - 1) * kFTU + f) * 4);
 #pragma unroll
               for (int r = 0; r < ER; ++r) v[r] = leaky(v[r] + bb);
               if (tid == 0) trace_ev(p, g * 4 + l - 1, 9);
@@ -635,7 +773,7 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
             constexpr int OUTS = 8;
             const int kq = f & 3, rp = (f >> 2) & 15, og = f >> 6;
             const uint32_t vrow = vt_a + (2 * rp) * kFTU * 4;
-            const uint32_t wrow = sp_a + (kSmLastW + og * OUTS * kFTU) * 4;
+            const uint32_t wrow = sp_a + (kSmLastW - C::kSmShift + og * OUTS * kFTU) * 4;
             const int osw = (og * OUTS) >> 2;  // (o >> 2) = osw + (oo >> 2)
 #pragma unroll
             for (int ps = 0; ps < ER / 32; ++ps) {
@@ -703,7 +841,7 @@ __global__ void __launch_bounds__(Cfg<RT>::kThreads, 1) flow_inverse_umma_kernel
           // ---- sum the team's partial sums in a fixed order (bitwise identical replicas), polling the data itself ----
           for (int i = tid; i < RT * 4; i += ET) {
             const int r = i >> 2, o4 = i & 3;
-            float4 acc = lds128(sp_a + (kSmLastB + 4 * o4) * 4);
+            float4 acc = lds128(sp_a + (kSmLastB - C::kSmShift + 4 * o4) * 4);
             const uint8_t* src = part_slot + ((size_t)pb * NT * RT + r) * kPartRowBytes + (2 * o4) * 16;
             const bool need0 = 2 * o4 < n_units, need1 = 2 * o4 + 1 < n_units;
             for (int c0 = 0; c0 < NT; c0 += 8) {
