@@ -317,7 +317,8 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
     f->smem128 = sizeof(umma::Smem<128>) + 1024;
     f->smem32j = sizeof(umma::Smem<32, true>) + 1024;
     // the just-in-time first layer needs every hidden layer to start at ring stage 0
-    f->jit = KCH % umma::Cfg<32, true>::kStages == 0 && f->smem32j <= (size_t)prop.sharedMemPerBlockOptin;
+    f->jit = KCH % umma::Cfg<32, true>::kStages == 0 && f->smem32j <= (size_t)prop.sharedMemPerBlockOptin &&
+             s2 + desc->dim_cond <= umma::kJitMaxK;
     if (const char* env = std::getenv("IKFLOW_B200_JIT")) f->jit = f->jit && std::atoi(env) != 0;  // A/B comparisons
   } else {
     f->smem32 = sizeof(FlowSmem<32>) + 1024;
@@ -438,7 +439,7 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
     fn = jit ? (const void*)umma::flow_inverse_umma_kernel<32, true>
              : rt == 32 ? (const void*)umma::flow_inverse_umma_kernel<32>
                         : rt == 64 ? (const void*)umma::flow_inverse_umma_kernel<64> : (const void*)umma::flow_inverse_umma_kernel<128>;
-    threads = rt == 32 ? umma::Cfg<32>::kThreads : rt == 64 ? umma::Cfg<64>::kThreads : umma::Cfg<128>::kThreads;
+    threads = jit ? umma::Cfg<32, true>::kThreads : rt == 32 ? umma::Cfg<32>::kThreads : rt == 64 ? umma::Cfg<64>::kThreads : umma::Cfg<128>::kThreads;
     smem = jit ? flow->smem32j : rt == 32 ? flow->smem32 : rt == 64 ? flow->smem64 : flow->smem128;
   } else {
     fn = rt == 32 ? (const void*)flow_inverse_kernel<32> : (const void*)flow_inverse_kernel<64>;

@@ -51,6 +51,7 @@ static_assert(kSmallBytesU % 16 == 0, "bulk copies move multiples of 16 bytes");
 // previous chunks are being multiplied.  No publish, no fence, no flag, no poll, no activation copy for that layer: one
 // of the three team exchanges of a subnet disappears.  The first-layer weights arrive with the stage:
 //   per (subnet, k-chunk): first_w [16 k][64 f] fp32 | first_b [64]
+constexpr int kJitMaxK = 12;                       // widest first-layer input (state half + condition) the JIT loop takes
 constexpr int kJitChunkFloats = kPad * kKC + kKC;  // 1088
 constexpr int kJitChunkBytes = kJitChunkFloats * 4;  // 4352
 static_assert(kJitChunkBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
@@ -80,7 +81,12 @@ struct Cfg {
   static constexpr int kLoaderWarp0 = kEpiWarps;  // first loader warp
   static constexpr int kMmaWarp = kEpiWarps + kLoaders;
   // registers are granted per 4 warps: up to 12 warps leave 170 registers per thread, 13+ would leave 128
-  static constexpr int kThreads = (kMmaWarp + 1) * 32;
+  // JIT: four more SIMT warps that only help with the just-in-time first layer (8 warps x 8 features per chunk)
+  static constexpr int kHelpers = JIT ? 4 : 0;
+  static constexpr int kHelperWarp0 = kMmaWarp + 1;
+  static constexpr int kGenWarps = kEpiWarps + kHelpers;
+  static constexpr int kGenThreads = 32 * kGenWarps;
+  static constexpr int kThreads = (kMmaWarp + 1 + kHelpers) * 32;
   static constexpr int kVtBytes = 32 * kFTU * 4;         // fp32 [32 rows][128 features] of one group: last-layer operand
   static constexpr int kTmemCols = 2 * RT <= 32 ? 32 : (2 * RT <= 64 ? 64 : (2 * RT <= 128 ? 128 : 256));  // D[:, 0:2RT]
   static_assert(kStage % 1024 == 0, "stages must keep the 1024-byte alignment of the swizzle atoms");
@@ -227,15 +233,79 @@ __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
 __device__ __forceinline__ void lds128_2x64(uint32_t a, uint64_t& v0, uint64_t& v1) {
   asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(v0), "=l"(v1) : "r"(a));
 }
+__device__ __forceinline__ uint64_t lds64(uint32_t a) {
+  uint64_t v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32u(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64u(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void sts128u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 template <int N>
 __device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
+// epilogue + helper warps of the just-in-time first layer
+template <int N>
+__device__ __forceinline__ void bar_gen() { asm volatile("bar.sync 5, %0;" ::"n"(N) : "memory"); }
+// the four warps of one generation group (0: epilogue warps, 1: helper warps)
+__device__ __forceinline__ void bar_gen_group(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(6 + grp) : "memory"); }
 // the 128 threads of one epilogue group
 __device__ __forceinline__ void bar_group(int h) { asm volatile("bar.sync %0, 128;" ::"r"(3 + h) : "memory"); }
 __device__ __forceinline__ void stg128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Just-in-time first layer, one 64-feature k-chunk, computed by a group of four warps: warp j of the group takes
+// features 16j .. 16j+15 of all 32 rows.  Lane = (row quad q = lane / 4, feature quad fq = lane % 4): rows q, q+8, q+16,
+// q+24 (inputs in registers) x features 16j + 4fq .. +3.  Per k ONE 128-bit shared load per lane (4 distinct addresses
+// per warp) -- shared memory is busy feeding the tensor core while this runs, every access is slow, so the loop is
+// written for few accesses, all issued up front.  fp32 FMAs (packed pairs) in the same order as the exchanged version:
+// bitwise identical activations.  LeakyReLU, bf16 head/tail split, 8-byte stores into the swizzled operand tile (rows
+// q + 8 rr: eight different swizzle phases per store instruction).
+template <int KB>
+__device__ __forceinline__ void jit_chunk_load(uint32_t stage_a, uint32_t w1off, int j, int lane, uint64_t (&w)[KB + 1][2]) {
+  const uint32_t w1_a = stage_a + w1off + (16 * j + 4 * (lane & 3)) * 4;
+  lds128_2x64(w1_a + (kPad * kKC) * 4, w[KB][0], w[KB][1]);  // bias
+#pragma unroll
+  for (int k = 0; k < KB; ++k) lds128_2x64(w1_a + (k * kKC) * 4, w[k][0], w[k][1]);
+}
+template <int KB, int APLANE>
+__device__ __forceinline__ void jit_chunk_compute(uint32_t stage_a, int j, int lane, const float (&x)[4][KB],
+                                                  const uint64_t (&w)[KB + 1][2]) {
+  const int q = lane >> 2, fq = lane & 3;
+  const int f0 = 16 * j + 4 * fq;
+  uint64_t acc[4][2];
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) acc[rr][0] = w[KB][0], acc[rr][1] = w[KB][1];
+#pragma unroll
+  for (int k = 0; k < KB; ++k) {
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const uint64_t xk = pack2(x[rr][k], x[rr][k]);
+      acc[rr][0] = ffma2(xk, w[k][0], acc[rr][0]);
+      acc[rr][1] = ffma2(xk, w[k][1], acc[rr][1]);
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    uint32_t hb[2], lb[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float a0, a1;
+      unpack2(acc[rr][c], a0, a1);
+      a0 = leaky(a0), a1 = leaky(a1);
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);  // .x = a0 (low half), one instruction
+      hb[c] = *reinterpret_cast<const uint32_t*>(&h2);
+      const __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - __uint_as_float(hb[c] << 16), a1 - __uint_as_float(hb[c] & 0xffff0000u));
+      lb[c] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    const uint32_t off = tile_off_bytes(q + 8 * rr, f0);
+    sts64u(stage_a + kWChunkU + off, hb[0], hb[1]);
+    sts64u(stage_a + kWChunkU + APLANE + off, lb[0], lb[1]);
+  }
 }
 
 template <int RT, bool JIT = false>
@@ -291,7 +361,57 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
   const int my_rgs = (p.n_rowgroups - slot + p.slots - 1) / p.slots;
   const int total_steps = my_rgs * steps_per_rg;
 
-  if (warp >= C::kLoaderWarp0 && warp < C::kLoaderWarp0 + C::kLoaders) {
+  // Just-in-time first layer of subnet step g: generation warp j (epilogue warps 0-3, helper warps 4-7) runs over the
+  // layer's k-chunks in ring order.  Called with the subnet's input in sm.a (bar_gen before the call).
+  auto jit_layer_loop_k = [&](auto kb, int grp, int j, int g) {
+    constexpr int KB = decltype(kb)::value;  // k extent (inputs and weights are zero-padded, fma(0, 0, acc) leaves acc as it is)
+    float xx[4][KB];                         // the inputs of this lane's four rows (lane / 4 + 8 rr)
+    const uint32_t xin = smem_u32(&sm.a[0][0]);
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+      for (int k4 = 0; k4 < KB; k4 += 4) {
+        const float4 xv = lds128(xin + (((lane >> 2) + 8 * rr) * kPad + k4) * 4);
+        xx[rr][k4] = xv.x, xx[rr][k4 + 1] = xv.y, xx[rr][k4 + 2] = xv.z, xx[rr][k4 + 3] = xv.w;
+      }
+    // the two groups take the chunks alternately: two chunks are always in the making, which hides the latency of
+    // the (busy) shared memory
+    for (int i = grp; i < KCH; i += 2) {
+      const int st = i % kStages;  // every layer starts at ring stage 0 (KCH % kStages == 0, checked at launch)
+      const uint32_t stage_a = smem_u32(sm.ring[st]);
+      // 1. the chunk's first-layer weights have landed: pull them into registers ...
+      mbar_wait(&sm.w1full[st], ((uint32_t)g * (uint32_t)(KCH / kStages) + (uint32_t)(i / kStages)) & 1u);
+      uint64_t w[KB + 1][2];
+      jit_chunk_load<KB>(stage_a, C::kW1Off, j, lane, w);
+      // 2. ... while waiting for the tensor core to let go of the stage's activation area (previous use of the stage)
+      const uint32_t use = ((uint32_t)g * (uint32_t)p.n_big * (uint32_t)KCH + (uint32_t)i) / kStages;
+      if (use > 0) mbar_wait(&sm.empty[st], (use - 1) & 1);
+      if (!(p.debug & 2048)) jit_chunk_compute<KB, C::kAPlane>(stage_a, j, lane, xx, w);
+      if (!(p.debug & 1024)) fence_proxy_async_smem();  // generic-proxy writes -> the tensor core's (async proxy) reads
+      bar_gen_group(grp);
+      if (j == 0 && lane == 0) {
+        mbar_arrive(&sm.full[st]);
+        mbar_arrive(&sm.w1empty[st]);
+        if (i == 0) trace_ev(p, g * 4, 4);
+      }
+    }
+  };
+  // Just-in-time first layer of subnet step g: warp j of generation group grp (0: epilogue warps, 1: helper warps).
+  // Called with the subnet's input in sm.a (bar_gen before the call).
+  // (first-layer inputs wider than kJitMaxK do not fit the register budget of this loop: such models take the
+  // exchanged first layer, see flow.cu)
+  auto jit_layer_loop = [&](int grp, int j, int g, int /*kin*/) { jit_layer_loop_k(std::integral_constant<int, kJitMaxK>{}, grp, j, g); };
+
+  if (JIT && warp >= C::kHelperWarp0) {
+    // ===== helper warps: nothing but the just-in-time first layer =====
+    if constexpr (JIT) {
+      for (int g = 0; g < total_steps; ++g) {
+        const int in_len = (g & 1) == 0 ? p.s1 : p.s2;  // steps alternate between the two subnets of a block
+        bar_gen<C::kGenThreads>();
+        jit_layer_loop(1, warp - C::kHelperWarp0, g, in_len + p.dim_cond);
+      }
+    }
+  } else if (warp >= C::kLoaderWarp0 && warp < C::kLoaderWarp0 + C::kLoaders) {
     // ===== loaders: bulk-TMA producers.  k-chunk number pos = ring_pos + i (counted over the whole launch) goes to ring
     // stage pos % kStages and is loaded by loader warp pos % kLoaders; warp 0 also prefetches the small parameters and
     // pulls the next layer's weights into L2.  Chunks are consumed in the fixed order kc = (2t + i) % KCH, so the
@@ -579,81 +699,10 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
 
           float v[ER];  // activations of feature f for the rows of this group
           if constexpr (JIT) {
-            // ---- first layer, just in time: thread = (row = lane, warp w -> features 16w .. 16w+15 of every 64-feature
-            //      k-chunk).  The row's input stays in registers, the chunk's weights are broadcast reads from the stage;
-            //      16 consecutive features of one row are two whole 16-byte units of the swizzled operand tile.  Same
-            //      fp32 FMA order as the exchanged version: bitwise identical activations. ----
+            // ---- first layer, just in time (see jit_chunk): the 4 epilogue warps and the 4 helper warps share every chunk ----
             if (tid == 0) trace_ev(p, g * 4, 10);
-            uint64_t xx[kPad];  // the row's inputs, each duplicated into both halves of a 64-bit pair
-#pragma unroll
-            for (int k4 = 0; k4 < kPad; k4 += 4) {
-              const float4 xv = lds128(xin_a + (lane * kPad + k4) * 4);
-              xx[k4] = pack2(xv.x, xv.x), xx[k4 + 1] = pack2(xv.y, xv.y), xx[k4 + 2] = pack2(xv.z, xv.z), xx[k4 + 3] = pack2(xv.w, xv.w);
-            }
-            const uint32_t unit_off[2] = {tile_off_bytes(lane, 16 * warp), tile_off_bytes(lane, 16 * warp + 8)};
-            for (int i = 0; i < KCH; ++i) {
-              const int st = i % kStages;  // every layer starts at ring stage 0 (KCH % kStages == 0, checked at launch)
-              {
-                // two conditions: the chunk's first-layer weights have landed, and the tensor core has let go of the
-                // stage's activation area (previous use of the stage).  Probe both before looking at either result.
-                const uint32_t w1par = ((uint32_t)g * (uint32_t)(KCH / kStages) + (uint32_t)(i / kStages)) & 1u;
-                const uint32_t use = ((uint32_t)g * (uint32_t)p.n_big * (uint32_t)KCH + (uint32_t)i) / kStages;
-                const long long t0 = clock64();
-                while (true) {
-                  const bool ok1 = mbar_try_wait(&sm.w1full[st], w1par);
-                  const bool ok2 = use == 0 || mbar_try_wait(&sm.empty[st], (use - 1) & 1);
-                  if (ok1 && ok2) break;
-                  if (clock64() - t0 > 4000000000LL) __trap();
-                }
-              }
-              const uint32_t stage_a = smem_u32(sm.ring[st]);
-              const uint32_t w1_a = stage_a + C::kW1Off + 16 * warp * 4;
-              // packed fp32 math (fma.rn.f32x2: two IEEE FMAs per instruction, same results as fmaf): 96 instead of 192
-              // issue slots per chunk -- this loop has to keep pace with the tensor core (one chunk per ~570 cycles)
-              uint64_t acc[8];
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) lds128_2x64(w1_a + (kPad * kKC + 4 * j4) * 4, acc[2 * j4], acc[2 * j4 + 1]);
-              // straight-line code (no branch per k: the loads of the next k must be free to move above the FMAs of this
-              // one); inputs and weights are zero-padded, and fma(0, 0, acc) leaves acc as it is
-              auto dot_k = [&](auto kb) {
-#pragma unroll
-                for (int k = 0; k < decltype(kb)::value; ++k) {
-#pragma unroll
-                  for (int j4 = 0; j4 < 4; ++j4) {
-                    uint64_t w01, w23;
-                    lds128_2x64(w1_a + (k * kKC + 4 * j4) * 4, w01, w23);
-                    acc[2 * j4] = ffma2(xx[k], w01, acc[2 * j4]);
-                    acc[2 * j4 + 1] = ffma2(xx[k], w23, acc[2 * j4 + 1]);
-                  }
-                }
-              };
-              if (kin <= 12) dot_k(std::integral_constant<int, 12>{});
-              else dot_k(std::integral_constant<int, kPad>{});
-              uint32_t hi[8], lo[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float a0, a1;
-                unpack2(acc[j], a0, a1);
-                a0 = leaky(a0), a1 = leaky(a1);
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);  // .x = a0 (low half), one instruction
-                const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
-                const __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - __uint_as_float(hb << 16), a1 - __uint_as_float(hb & 0xffff0000u));
-                hi[j] = hb;
-                lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
-              }
-#pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                sts128u(stage_a + kWChunkU + unit_off[u], hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
-                sts128u(stage_a + kWChunkU + C::kAPlane + unit_off[u], lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
-              }
-              fence_proxy_async_smem();  // generic-proxy writes -> the tensor core's (async proxy) reads
-              bar_epi<ET>();
-              if (tid == 0) {
-                mbar_arrive(&sm.full[st]);
-                mbar_arrive(&sm.w1empty[st]);
-                if (i == 0) trace_ev(p, g * 4, 4);
-              }
-            }
+            bar_gen<C::kGenThreads>();  // the helpers may read the subnet's input
+            jit_layer_loop(0, warp, g, kin);
           } else {
           // ---- first layer: fp32 FMA ----
             const float b0 = lds32(sp_a + (kSmFirstB - C::kSmShift + f) * 4);

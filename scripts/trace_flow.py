@@ -78,7 +78,7 @@ if os.environ.get('IKFLOW_B200_DEBUG') == '4':
     print("just-in-time first layer, CTA 0 (cycles rel. to chunk 0 start): start / W1 landed / stage free / math+stores done / barrier passed")
     for layer in (6, 10):
         base = int(sa[0, layer, 16])
-        for nm, lo in (("start", 16), ("w1", 32), ("free", 48), ("math", 64), ("bar", 80)):
+        for nm, lo in (("start", 16), ("ready", 32)):
             print(f"  layer {layer} {nm:>6s} " + " ".join(f"{int(v) - base:6d}" for v in sa[0, layer, lo:lo + 16]))
 
 # phase summary, averaged over subnets 1.. and the CTAs of the team
