@@ -76,7 +76,9 @@ struct Cfg {
   static constexpr int kStages = RT == 32 ? 4 : (RT == 64 ? 3 : 2);
   // loader warp w owns the ring stages s with s % kLoaders == w: its waits on a stage's barriers are then strictly in
   // order (a waiter may lag an mbarrier by at most one phase)
-  static constexpr int kLoaders = kStages < kLoaderWarps ? kStages : kLoaderWarps;
+  // JIT: two loader warps (each owns two stages), so that the CTA stays at 11 warps: with 13 the register file grants
+  // only 128 registers per thread and the epilogue spills
+  static constexpr int kLoaders = JIT ? 2 : (kStages < kLoaderWarps ? kStages : kLoaderWarps);
   static_assert(kStages % kLoaders == 0, "every stage needs exactly one owner");
   static constexpr int kLoaderWarp0 = kEpiWarps;  // first loader warp
   static constexpr int kMmaWarp = kEpiWarps + kLoaders;
