@@ -336,13 +336,13 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"], "traffic": 204_991_232 + 4_015_616 if args.model == "panda__full__lp191_5.25m" and B == 512 else None,
+                "frac": achieved / peaks["bf16_tflops"], "traffic": 205_541_376 + 3_670_272 if args.model == "panda__full__lp191_5.25m" and B == 512 else None,
                 "peak_source": peaks["source"] + ", burst bf16",
-                "kernel": "ikf::umma::flow_inverse_umma_kernel<%d>" % (32 if B <= 576 else 64 if B <= 1152 else 128), "kernel_ms": kernel_ms,
+                "kernel": "ikf::umma::flow_inverse_umma_kernel<%s>" % (("32, true" if width - width // 2 + 8 <= 12 else "32") if B <= 576 else "64" if B <= 1152 else "128"), "kernel_ms": kernel_ms,
                 "algorithmic_flops_per_launch": fl * B,
                 "hbm": {"algorithmic_bytes_per_launch": wbytes + B * 84, "achieved_gbs": (wbytes + B * 84) / (kernel_ms * 1e-3) / 1e9,
                         "peak_gbs": peaks["hbm_gbs"], "frac": (wbytes + B * 84) / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-                "traffic_note": "dram__bytes_read+write of one launch, profiles/r1_flow_umma_b512_ncu_summary.txt (ncu --set full)",
+                "traffic_note": "dram__bytes_read+write of one launch, profiles/r1b_flow_umma_b512_ncu_summary.txt (ncu --set full)",
             },
             "status_word": status,
         }
