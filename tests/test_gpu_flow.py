@@ -247,3 +247,39 @@ def test_every_engine_and_row_group_size(engine, rt, batch, monkeypatch):
     out = model.inverse(latent.to(DEV), cond.to(DEV))
     assert (out.cpu() - _oracle(sd, hp, latent, cond)).abs().max() < TOL
     assert model.status() == 0
+
+
+@pytest.mark.parametrize("batch", [1, 37, 512, 576])
+def test_jit_first_layer_is_bitwise_identical_to_the_exchanged_one(batch, monkeypatch):
+    """32-row groups of the tcgen05 engine compute the first layer of every subnet just in time, for all hidden features,
+    in every CTA (no exchange).  Same fp32 FMA order as the exchanged version (IKFLOW_B200_JIT=0): identical bits."""
+    hp = IkflowModelParameters()
+    hp.nb_nodes, hp.dim_latent_space = 12, 7
+    robot = ikflow_b200.Panda()
+    sd = make_synthetic_state_dict(hp, robot.actuated_joints_limits, seed=0)
+    latent, poses, cond = _inputs(batch, 7)
+    outs = []
+    for jit in ("1", "0"):
+        monkeypatch.setenv("IKFLOW_B200_JIT", jit)
+        model = ikflow_b200.glow_cNF_model(hp, robot, 8, 7)
+        model.load_state_dict(sd)
+        outs.append(model.inverse(latent.to(DEV), cond.to(DEV)).clone())
+        assert model.status() == 0
+    assert torch.equal(outs[0], outs[1])
+    assert (outs[0].cpu() - _oracle(sd, hp, latent, cond)).abs().max() < TOL
+
+
+def test_jit_kernel_with_several_row_groups_per_team(monkeypatch):
+    """More 32-row groups than team slots (forced with IKFLOW_B200_RT): every team walks several row groups, the ring
+    and the first-layer weight hand-over keep their phase across them."""
+    monkeypatch.setenv("IKFLOW_B200_RT", "32")
+    hp = IkflowModelParameters()
+    hp.nb_nodes, hp.dim_latent_space = 4, 7
+    robot = ikflow_b200.Panda()
+    sd = make_synthetic_state_dict(hp, robot.actuated_joints_limits, seed=0)
+    model = ikflow_b200.glow_cNF_model(hp, robot, 8, 7)
+    model.load_state_dict(sd)
+    latent, poses, cond = _inputs(1500, 7)
+    out = model.inverse(latent.to(DEV), cond.to(DEV))
+    assert (out.cpu() - _oracle(sd, hp, latent, cond)).abs().max() < TOL
+    assert model.status() == 0
