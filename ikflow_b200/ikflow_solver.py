@@ -241,7 +241,18 @@ class IKFlowSolver:
             return solutions, valids
 
     def load_state_dict(self, state_dict_filename: str):
-        """Set the nn_models state_dict from a pickled FrEIA state dict (``ikflow_solver.py:413-441``)."""
+        """Set the nn_models state_dict from a pickled FrEIA state dict (``ikflow_solver.py:413-441``), or from the
+        pickle-free ``.ikfw`` container of :mod:`ikflow_b200.weight_files` (same numbers, versioned + checksummed)."""
+        if str(state_dict_filename).endswith(".ikfw"):
+            from .weight_files import load_ikfw
+
+            state_dict, params, dim_cond, ndof = load_ikfw(state_dict_filename)
+            mine = (self._network_width, self.dim_cond, self.nn_model.nb_nodes, self.nn_model.coeff_fn_config, self.nn_model.hidden, self.ndof)
+            theirs = (params.dim_latent_space, dim_cond, params.nb_nodes, params.coeff_fn_config, params.coeff_fn_internal_size, ndof)
+            assert mine == theirs, f"{state_dict_filename} describes {theirs}, this solver was built for {mine} (width, dim_cond, nb_nodes, coeff_fn_config, hidden, ndof)"
+            self.nn_model.load_state_dict(state_dict)
+            self._model_weights_loaded = True
+            return
         with open(state_dict_filename, "rb") as f:
             try:
                 state_dict = pickle.load(f)
