@@ -87,6 +87,8 @@ struct IkfFlow {
   size_t blob_bytes = 0, big_w_bytes = 0;
   ikf::FlowParams base;  // pointers + model constants; per-call fields filled at launch
   size_t smem32 = 0, smem64 = 0, smem128 = 0, smem32j = 0;
+  float logdet_m = 0.f;  // FixedLinearTransform.logDetM (forward pass)
+  float* m_fwd_dev = nullptr;  // device [kPad][kPad], inside blob
   bool jit = false;  // umma engine, 32-row groups: first layer computed just in time by every CTA (flow_umma.cuh)
   int engine = 0;  // 0 = mma.sync tiles (flow_mma.cuh), 1 = tcgen05 / TMEM (flow_umma.cuh)
   uint32_t epoch = 1;  // doubles as launch id; 0 is "no launch aborted"
@@ -263,7 +265,7 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
       }
   }
 
-  std::vector<int> perm(nb * kPad, 0);
+  std::vector<int> perm(2 * nb * kPad, 0);  // [nb][kPad] perm_inv, then [nb][kPad] perm (its inverse; forward pass)
   for (int i = 0; i < nb; ++i)
     for (int j = 0; j < W; ++j) {
       const int64_t v = perm_inv[(size_t)i * W + j];
@@ -272,8 +274,44 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
         return fail(IKF_EINVAL, "ikf_flow_create: perm_inv[%d][%d]=%lld out of range", i, j, (long long)v);
       }
       perm[i * kPad + j] = (int)v;
+      perm[(nb + i) * kPad + (int)v] = j;  // perm[perm_inv[j]] = j
     }
-  std::vector<float> consts(kPad * kPad + 3 * kPad, 0.f);
+  std::vector<float> consts(2 * kPad * kPad + 3 * kPad, 0.f);  // M_inv | b | lo | hi | M
+  {
+    // FixedLinearTransform forward needs M = M_inv^-1 and logDetM = log|det M|: Gauss-Jordan in double (W <= 16);
+    // ikf_flow_set_forward_tables replaces both by the stored parameters
+    std::vector<double> a((size_t)W * 2 * W, 0.0);
+    for (int i = 0; i < W; ++i) {
+      for (int j = 0; j < W; ++j) a[(size_t)i * 2 * W + j] = m_inv[(size_t)i * W + j];
+      a[(size_t)i * 2 * W + W + i] = 1.0;
+    }
+    double logdet_inv = 0.0;
+    bool singular = false;
+    for (int c = 0; c < W && !singular; ++c) {
+      int piv = c;
+      for (int r = c + 1; r < W; ++r)
+        if (std::fabs(a[(size_t)r * 2 * W + c]) > std::fabs(a[(size_t)piv * 2 * W + c])) piv = r;
+      if (a[(size_t)piv * 2 * W + c] == 0.0) { singular = true; break; }
+      if (piv != c)
+        for (int j = 0; j < 2 * W; ++j) std::swap(a[(size_t)piv * 2 * W + j], a[(size_t)c * 2 * W + j]);
+      const double d = a[(size_t)c * 2 * W + c];
+      logdet_inv += std::log(std::fabs(d));
+      for (int j = 0; j < 2 * W; ++j) a[(size_t)c * 2 * W + j] /= d;
+      for (int r = 0; r < W; ++r) {
+        if (r == c) continue;
+        const double m = a[(size_t)r * 2 * W + c];
+        if (m != 0.0)
+          for (int j = 0; j < 2 * W; ++j) a[(size_t)r * 2 * W + j] -= m * a[(size_t)c * 2 * W + j];
+      }
+    }
+    if (singular) {
+      delete f;
+      return fail(IKF_EINVAL, "ikf_flow_create: M_inv is singular");
+    }
+    for (int i = 0; i < W; ++i)
+      for (int j = 0; j < W; ++j) consts[kPad * kPad + 3 * kPad + i * kPad + j] = (float)a[(size_t)i * 2 * W + W + j];
+    f->logdet_m = (float)(-logdet_inv);
+  }
   for (int i = 0; i < W; ++i)
     for (int j = 0; j < W; ++j) consts[i * kPad + j] = m_inv[(size_t)i * W + j];
   for (int j = 0; j < W; ++j) consts[kPad * kPad + j] = flt_b[j];
@@ -367,7 +405,10 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   p.small = (const float*)(base + off_small);
   p.first_jit = engine ? (const float*)(base + off_jit) : nullptr;
   p.perm_inv = (const int*)(base + off_perm);
+  p.perm_fwd = p.perm_inv + (size_t)nb * kPad;
   p.m_inv = (const float*)(base + off_consts);
+  p.m_fwd = p.m_inv + kPad * kPad + 3 * kPad;
+  f->m_fwd_dev = (float*)(base + off_consts) + kPad * kPad + 3 * kPad;
   p.flt_b = p.m_inv + kPad * kPad;
   p.lo = p.flt_b + kPad;
   p.hi = p.lo + kPad;
@@ -387,7 +428,7 @@ int ikf_flow_reserve(IkfFlow* flow, int max_batch) {
 
 static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* cond, int cond_ld, int cond_rows,
                        int cond_cols, float* out, int out_ld, int out_cols, int batch, int block_first, int block_last,
-                       int finalize, int clamp, void* stream, const char* name) {
+                       int finalize, int clamp, void* stream, const char* name, int forward = 0, float* logdet_out = nullptr) {
   if (!flow) return fail(IKF_EINVAL, "%s: flow is NULL", name);
   if (batch < 0) return fail(IKF_EINVAL, "%s: negative batch %d", name, batch);
   if (batch == 0) return IKF_OK;
@@ -407,6 +448,8 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   p.in = in; p.in_ld = in_ld; p.cond = cond; p.cond_ld = cond_ld; p.cond_rows = cond_rows; p.cond_cols = cond_cols;
   p.out = out; p.out_ld = out_ld; p.out_cols = out_cols; p.batch = batch;
   p.block_first = block_first; p.block_last = block_last; p.finalize = finalize; p.clamp_out = clamp;
+  p.forward = forward; p.logdet_out = logdet_out; p.logdet_m = flow->logdet_m;
+  if (forward && !flow->engine) return fail(IKF_EINVAL, "%s: the forward pass is implemented by the tcgen05 engine only (hidden %% 128 == 0, hidden <= 1024, coeff_fn_config >= 2)", name);
   // Row groups of 32 while that still fits in one wave of teams (more CTAs in flight, and a partner CTA on every SM
   // to compute while a team waits on an exchange), 64 beyond.
   int rt = ((batch + 31) / 32 <= flow->slots_max) ? 32 : 64;
@@ -465,6 +508,26 @@ int ikf_flow_inverse_blocks(IkfFlow* flow, const float* state_in, int in_ld, con
   if (!flow) return fail(IKF_EINVAL, "ikf_flow_inverse_blocks: flow is NULL");
   return flow_launch(flow, state_in, in_ld, cond, cond_ld, cond_rows, cond_cols, state_out, out_ld,
                      flow->desc.ndim_tot, batch, block_first, block_last, 0, 0, stream, "ikf_flow_inverse_blocks");
+}
+
+int ikf_flow_forward(IkfFlow* flow, const float* x, int x_ld, const float* cond, int cond_ld, int cond_rows, int cond_cols,
+                     float* z_out, int out_ld, float* logdet_out, int batch, void* stream) {
+  if (!flow) return fail(IKF_EINVAL, "ikf_flow_forward: flow is NULL");
+  return flow_launch(flow, x, x_ld, cond, cond_ld, cond_rows, cond_cols, z_out, out_ld, flow->desc.ndim_tot, batch,
+                     flow->desc.nb_nodes - 1, 0, 0, 0, stream, "ikf_flow_forward", 1, logdet_out);
+}
+
+int ikf_flow_set_forward_tables(IkfFlow* flow, const float* m, float log_det_m) {
+  if (!flow || !m) return fail(IKF_EINVAL, "ikf_flow_set_forward_tables: bad arguments");
+  DeviceGuard guard(flow->device);
+  if (!guard.ok) return fail(IKF_ECUDA, "ikf_flow_set_forward_tables: cudaSetDevice(%d) failed", flow->device);
+  const int W = flow->desc.ndim_tot;
+  std::vector<float> padded(kPad * kPad, 0.f);
+  for (int i = 0; i < W; ++i)
+    for (int j = 0; j < W; ++j) padded[i * kPad + j] = m[(size_t)i * W + j];
+  IKF_CUDA(cudaMemcpy(flow->m_fwd_dev, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice));
+  flow->logdet_m = log_det_m;
+  return IKF_OK;
 }
 
 int ikf_flow_status(IkfFlow* flow, void* stream, uint32_t* status_out) {

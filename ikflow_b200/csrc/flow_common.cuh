@@ -45,6 +45,8 @@ struct FlowParams {
   const float* small;          // [subnet][NT t][kSmallFloats]
   const float* first_jit;      // umma engine: [subnet][KCH c][16 k][64 f] + [64] bias per chunk (just-in-time first layer)
   const int* perm_inv;         // [nb_nodes][kPad]
+  const int* perm_fwd;         // [nb_nodes][kPad]: PermuteRandom.perm (forward pass)
+  const float* m_fwd;          // [kPad][kPad]: FixedLinearTransform M, out_j = sum_i x_i m_fwd[i][j] + b_j (forward pass)
   const float* m_inv;          // [kPad][kPad]  out_j = sum_i (u_i - b_i) m_inv[i][j]
   const float* flt_b;          // [kPad]
   const float* lo;             // [kPad] joint limits
@@ -63,6 +65,9 @@ struct FlowParams {
   float* out;
   int in_ld, cond_ld, cond_rows, cond_cols, out_ld, out_cols;
   int batch, block_first, block_last, finalize, clamp_out, n_rowgroups, slots;
+  int forward;         // 1: x -> z with log-det (blocks block_last..block_first ascending), tcgen05 engine only
+  float logdet_m;      // FixedLinearTransform.logDetM
+  float* logdet_out;   // [batch] (forward pass)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -103,6 +103,7 @@ struct __align__(1024) Smem {
   float small[2][C::kSmFloats];
   float u[RT][kPad];  // flow state
   float cnd[RT][8];
+  float logdet[RT];  // forward pass: log|det J| accumulated over the blocks
   // input of the current subnet [state half | condition | 0] at its start, output of its last layer at its end
   float a[RT][kPad];
   uint64_t full[C::kStages], empty[C::kStages];
@@ -365,6 +366,12 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
 
   // Just-in-time first layer of subnet step g: generation warp j (epilogue warps 0-3, helper warps 4-7) runs over the
   // layer's k-chunks in ring order.  Called with the subnet's input in sm.a (bar_gen before the call).
+  // Subnet evaluated at step g of a row group.  Reverse pass (z -> x): blocks block_first .. block_last descending,
+  // subnet1 then subnet2; forward pass (x -> z, FrEIA GLOWCouplingBlock.forward): blocks ascending, subnet2 then subnet1.
+  auto step_block = [&](int g) { return p.forward ? p.block_last + (g % steps_per_rg) / 2 : p.block_first - (g % steps_per_rg) / 2; };
+  auto step_sidx = [&](int g) { return p.forward ? 1 - (g & 1) : (g & 1); };  // steps_per_rg is even
+  auto step_subnet = [&](int g) { return 2 * step_block(g) + step_sidx(g); };
+
   auto jit_layer_loop_k = [&](auto kb, int grp, int j, int g) {
     constexpr int KB = decltype(kb)::value;  // k extent (inputs and weights are zero-padded, fma(0, 0, acc) leaves acc as it is)
     float xx[4][KB];                         // the inputs of this lane's four rows (lane / 4 + 8 rr)
@@ -408,7 +415,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
     // ===== helper warps: nothing but the just-in-time first layer =====
     if constexpr (JIT) {
       for (int g = 0; g < total_steps; ++g) {
-        const int in_len = (g & 1) == 0 ? p.s1 : p.s2;  // steps alternate between the two subnets of a block
+        const int in_len = step_sidx(g) == 0 ? p.s1 : p.s2;  // steps alternate between the two subnets of a block
         bar_gen<C::kGenThreads>();
         jit_layer_loop(1, warp - C::kHelperWarp0, g, in_len + p.dim_cond);
       }
@@ -427,8 +434,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
       const int b = g & 1;
       if (g >= 2) mbar_wait_relaxed(&sm.small_empty[b], ((g >> 1) - 1) & 1);
       if (lane == 0) {
-        const int in_rg = g % steps_per_rg;
-        const int n = 2 * (p.block_first - in_rg / 2) + (in_rg & 1);
+        const int n = step_subnet(g);
         mbar_arrive_expect_tx(&sm.small_full[b], C::kSmFloats * 4);
         bulk_g2s(sm.small[b], p.small + ((size_t)n * NT + t) * kSmallFloatsU + C::kSmShift, C::kSmFloats * 4, &sm.small_full[b]);
       }
@@ -441,8 +447,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
     auto prefetch_layer = [&](int q) {
       const int g2 = q / p.n_big, l2 = q % p.n_big;
       if (g2 >= total_steps) return;
-      const int in_rg2 = g2 % steps_per_rg;
-      const int n2 = 2 * (p.block_first - in_rg2 / 2) + (in_rg2 & 1);
+      const int n2 = step_subnet(g2);
       const uint8_t* wnext =
           reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n2 * p.n_big + l2) * NT + t) * KCH * kWChunkU;
       // ... plus, whatever the team, the first bytes of the chunks this CTA loads first (kc = 2t .. 2t+3): the address
@@ -455,8 +460,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
     if (lw == 0) prefetch_small(0);
     bool gave_up = false;
     for (int g = 0; g < total_steps; ++g) {
-      const int in_rg = g % steps_per_rg;
-      const int n = 2 * (p.block_first - in_rg / 2) + (in_rg & 1);
+      const int n = step_subnet(g);
       for (int l = 0; l < p.n_big; ++l) {
         const int buf = xchg & 1;
         const uint32_t expected = p.epoch + 1 + act_w[buf];
@@ -667,6 +671,24 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
     const int j8 = lane & 7;     // publish: row inside an 8-row block after the lane transpose
     const uint32_t xin_a = smem_u32(&sm.a[0][0]);
 
+    // u <- u[:, table]
+    auto permute_state = [&](const int* table) {
+      constexpr int kPer = (RT * kPad + ET - 1) / ET;
+      float tmp[kPer];
+#pragma unroll
+      for (int c = 0; c < kPer; ++c) {
+        const int i = tid + c * ET;
+        tmp[c] = i < RT * p.W ? sm.u[i / p.W][table[i % p.W]] : 0.f;
+      }
+      bar_epi<ET>();
+#pragma unroll
+      for (int c = 0; c < kPer; ++c) {
+        const int i = tid + c * ET;
+        if (i < RT * p.W) sm.u[i / p.W][i % p.W] = tmp[c];
+      }
+      bar_epi<ET>();
+    };
+
     int g = 0;
     for (int rg = slot; rg < p.n_rowgroups; rg += p.slots) {
       for (int i = tid; i < RT * kPad; i += ET) {
@@ -681,9 +703,35 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
         if (j < 8) sm.cnd[r][j] = cv;
       }
       bar_epi<ET>();
+      if (p.forward) {
+        // FixedLinearTransform forward, x.mm(M) + b (FrEIA; ikflow/model.py:197), and a fresh log-det accumulator
+        constexpr int kPer = (RT * kPad + ET - 1) / ET;
+        float tmp[kPer];
+#pragma unroll
+        for (int c = 0; c < kPer; ++c) {
+          const int i = tid + c * ET, r = i / kPad, j = i % kPad;
+          float o = 0.f;
+          if (i < RT * kPad && j < p.W) {
+            for (int k = 0; k < p.W; ++k) o = fmaf(sm.u[r][k], p.m_fwd[k * kPad + j], o);
+            o += p.flt_b[j];
+          }
+          tmp[c] = o;
+        }
+        bar_epi<ET>();
+#pragma unroll
+        for (int c = 0; c < kPer; ++c) {
+          const int i = tid + c * ET;
+          if (i < RT * kPad) sm.u[i / kPad][i % kPad] = tmp[c];
+        }
+        for (int r = tid; r < RT; r += ET) sm.logdet[r] = p.logdet_m;
+        bar_epi<ET>();
+      }
 
-      for (int blk = p.block_first; blk >= p.block_last; --blk) {
-        for (int sidx = 0; sidx < 2; ++sidx, ++g) {
+      for (int bi = 0; bi < n_blocks; ++bi) {
+        const int blk = p.forward ? p.block_last + bi : p.block_first - bi;
+        if (p.forward) permute_state(p.perm_fwd + blk * kPad);  // PermuteRandom forward: x[:, perm], before the block
+        for (int step = 0; step < 2; ++step, ++g) {
+          const int sidx = p.forward ? 1 - step : step;
           const int sb = g & 1;
           const uint32_t sp_a = smem_u32(sm.small[sb]);  // explicit shared-space accesses (see lds128)
           const int in_off = sidx == 0 ? 0 : p.s1;
@@ -949,27 +997,18 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
             const int r = i / tg_len, j = i % tg_len;
             const float sc = p.clamp_scale * atanf(sm.a[r][j]);
             const float tr = sm.a[r][tg_len + j];
-            sm.u[r][tg_off + j] = (sm.u[r][tg_off + j] - tr) * expf(-sc);
+            sm.u[r][tg_off + j] = p.forward ? fmaf(sm.u[r][tg_off + j], expf(sc), tr) : (sm.u[r][tg_off + j] - tr) * expf(-sc);
           }
+          if (p.forward)  // log-det of the block: sum of the (clamped) scales, one thread per row, fixed order
+            for (int r = tid; r < RT; r += ET) {
+              float acc = sm.logdet[r];
+              for (int j = 0; j < tg_len; ++j) acc += p.clamp_scale * atanf(sm.a[r][j]);
+              sm.logdet[r] = acc;
+            }
           bar_epi<ET>();
           if (tid == 0) trace_ev(p, g * 4 + 3, 13);
         }
-        {
-          constexpr int kPer = (RT * kPad + ET - 1) / ET;
-          float tmp[kPer];
-#pragma unroll
-          for (int c = 0; c < kPer; ++c) {
-            const int i = tid + c * ET;
-            tmp[c] = i < RT * p.W ? sm.u[i / p.W][p.perm_inv[blk * kPad + i % p.W]] : 0.f;
-          }
-          bar_epi<ET>();
-#pragma unroll
-          for (int c = 0; c < kPer; ++c) {
-            const int i = tid + c * ET;
-            if (i < RT * p.W) sm.u[i / p.W][i % p.W] = tmp[c];
-          }
-          bar_epi<ET>();
-        }
+        if (!p.forward) permute_state(p.perm_inv + blk * kPad);  // PermuteRandom reverse: x[:, perm_inv], after the block
       }
 
       if (t == 0) {
@@ -988,6 +1027,9 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
           if (!isfinite(o)) atomicOr(p.status, IKF_STATUS_NONFINITE);
           p.out[(size_t)row * p.out_ld + j] = o;
         }
+        if (p.forward && p.logdet_out != nullptr)
+          for (int r = tid; r < RT; r += ET)
+            if (rg * RT + r < p.batch) p.logdet_out[rg * RT + r] = sm.logdet[r];
       }
       bar_epi<ET>();
     }

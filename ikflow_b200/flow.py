@@ -133,6 +133,9 @@ class FlowModel:
                 flt_b.ctypes.data, lo.ctypes.data, hi.ctypes.data, idx, ctypes.byref(out),
             )
             _lib.check(code, "ikf_flow_create")
+            # forward pass: the stored FixedLinearTransform parameters instead of the library's own M_inv^-1
+            m = np.ascontiguousarray(sd["module_list.0.M"].to(torch.float32).numpy())
+            _lib.check(_lib.lib().ikf_flow_set_forward_tables(out, m.ctypes.data, float(sd["module_list.0.logDetM"])), "ikf_flow_set_forward_tables")
             self._handles[idx] = out.value
         return self._handles[idx]
 
@@ -170,6 +173,22 @@ class FlowModel:
         _lib.check(code, "ikf_flow_inverse")
         return out
 
+    def forward_pass(self, x: torch.Tensor, cond: torch.Tensor):
+        """x -> z with its log-determinant, ``nn_model(x, c=cond, rev=False)`` (``ikflow/training/lt_model.py:156``), in one
+        launch.  Inference only: no gradients flow through it."""
+        self._check_inputs(x, cond, self.ndim_tot, self.dim_cond)
+        batch = x.shape[0]
+        assert cond.shape[0] >= 1 and batch % cond.shape[0] == 0, f"{batch} rows vs {cond.shape[0]} condition rows"
+        x, cond = x.contiguous(), cond.contiguous()
+        z = torch.empty((batch, self.ndim_tot), dtype=torch.float32, device=x.device)
+        logdet = torch.empty((batch,), dtype=torch.float32, device=x.device)
+        code = _lib.lib().ikf_flow_forward(
+            self._handle(x.device), x.data_ptr(), x.stride(0), cond.data_ptr(), cond.stride(0), cond.shape[0], cond.shape[1],
+            z.data_ptr(), z.stride(0), logdet.data_ptr(), batch, torch.cuda.current_stream(x.device).cuda_stream,
+        )
+        _lib.check(code, "ikf_flow_forward")
+        return z, logdet
+
     def inverse_blocks(self, state: torch.Tensor, cond: torch.Tensor, block_first: int, block_last: int) -> torch.Tensor:
         """Coupling blocks block_first, block_first-1, ..., block_last of the reverse pass (each followed by its
         permutation); no FixedLinearTransform, no clamp."""
@@ -199,18 +218,17 @@ class FlowModel:
         return {"packed_weight_bytes": nbytes.value, "grid_ctas_last": grid.value, "smem_bytes": smem.value}
 
     def __call__(self, x_or_z: torch.Tensor, c=None, rev: bool = False, jac: bool = True):
-        """``GraphINN.forward`` as the solver uses it.  Returns ``(out [n x ndim_tot], logdet)``; the log-determinant
-        is not computed in the reverse direction (the solver discards it, ``ikflow_solver.py:98``) and is returned as
-        ``None``."""
-        if not rev:
-            raise NotImplementedError(
-                "ikflow_b200 implements the inference direction (rev=True); the x->z training pass is out of scope"
-            )
+        """``GraphINN.forward``.  Returns ``(out [n x ndim_tot], logdet)``.  ``rev=True`` (what the solver uses,
+        ``ikflow_solver.py:98``): the log-determinant is not computed (the solver discards it) and is returned as
+        ``None``.  ``rev=False``: z and log|det dz/dx| (``None`` with ``jac=False``), inference only."""
         if isinstance(c, (list, tuple)):
             assert len(c) == 1
             c = c[0]
         assert c is not None, "the flow is conditional: pass c=[n x dim_cond]"
         assert x_or_z.shape[0] == c.shape[0], f"{x_or_z.shape[0]} != {c.shape[0]}"
+        if not rev:
+            z, logdet = self.forward_pass(x_or_z, c)
+            return z, (logdet if jac else None)
         return self.inverse(x_or_z, c), None
 
     forward = __call__

@@ -112,6 +112,21 @@ int ikf_flow_inverse_blocks(IkfFlow* flow, const float* state_in, int in_ld, con
                             int cond_rows, int cond_cols, float* state_out, int out_ld, int batch, int block_first,
                             int block_last, void* stream);
 
+/* Forward pass (x -> z) with its log-determinant -- nn_model(x, c=cond, rev=False) of the reference
+ * (ikflow/training/lt_model.py:129-159 ml_loss_fn; tests/model_test.py:117-177): FixedLinearTransform (x.mm(M) + b), then
+ * for i = 0 .. nb_nodes-1: PermuteRandom_i (x[:, perm_i]) and GLOWCouplingBlock_i forward (subnet2 first).  Inference
+ * only (no gradients).  tcgen05 engine only (IKF_EINVAL otherwise).
+ *   x        [batch][ndim_tot]  (row stride x_ld floats)        cond as for ikf_flow_inverse
+ *   z_out    [batch][ndim_tot]  (row stride out_ld floats)
+ *   logdet_out [batch] or NULL: log|det dz/dx| = logDetM + sum over blocks of the clamped scales */
+int ikf_flow_forward(IkfFlow* flow, const float* x, int x_ld, const float* cond, int cond_ld, int cond_rows, int cond_cols,
+                     float* z_out, int out_ld, float* logdet_out, int batch, void* stream);
+
+/* Optional: the stored FixedLinearTransform parameters M [ndim_tot][ndim_tot] (row-major, "module_list.0.M", HOST
+ * pointer) and logDetM for the forward pass.  Without this call ikf_flow_create's own M = M_inv^-1 (double precision
+ * Gauss-Jordan) and log|det M| are used. */
+int ikf_flow_set_forward_tables(IkfFlow* flow, const float* m, float log_det_m);
+
 /* Reads (and clears) the device status word.  SYNCHRONISES `stream`. */
 int ikf_flow_status(IkfFlow* flow, void* stream, uint32_t* status_out);
 

@@ -283,3 +283,48 @@ def test_jit_kernel_with_several_row_groups_per_team(monkeypatch):
     out = model.inverse(latent.to(DEV), cond.to(DEV))
     assert (out.cpu() - _oracle(sd, hp, latent, cond)).abs().max() < TOL
     assert model.status() == 0
+
+
+# ---- forward pass (x -> z) with log-det: SURVEY.md 8f rank 4 --------------------------------------------------------
+@pytest.mark.parametrize("batch,nb,w", [(1, 12, 7), (100, 12, 7), (512, 12, 7), (700, 4, 7), (1500, 3, 7), (300, 16, 10)])
+def test_forward_pass_matches_the_oracle(batch, nb, w):
+    """``nn_model(x, c=cond, rev=False)`` (``ikflow/training/lt_model.py:156``): z and log|det| against the oracle's
+    FrEIA restatement, x = joint-angle-like samples (the flow's data side), every row-group size incl. the JIT kernel."""
+    solver, hp, sd = _solver(nb, w, 3, 1024, "panda" if w == 7 else "fetch_arm")
+    g = torch.Generator().manual_seed(7)
+    x = (torch.rand(batch, w, generator=g) * 2 - 1) * 2.0
+    _, poses, cond = _inputs(batch, w)
+    z, logdet = solver.nn_model(x.to(DEV), c=cond.to(DEV), rev=False)
+    z_ref, ld_ref = freia_flow.flow_forward(sd, x, cond, hp.nb_nodes, hp.coeff_fn_config, hp.rnvp_clamp)
+    scale = max(1.0, float(z_ref.abs().max()))
+    assert (z.cpu() - z_ref).abs().max() < TOL * scale, ((z.cpu() - z_ref).abs().max(), scale)
+    assert (logdet.cpu() - ld_ref).abs().max() < 1e-3
+    assert solver.nn_model.status() == 0
+    z2, none = solver.nn_model(x.to(DEV), c=cond.to(DEV), rev=False, jac=False)
+    assert none is None and torch.equal(z2, z)
+
+
+def test_forward_then_reverse_is_the_identity():
+    """The reference's invertibility property (tests/model_test.py: forward and reverse passes of the same graph)."""
+    solver, hp, sd = _solver(12, 7, 3, 1024)
+    g = torch.Generator().manual_seed(11)
+    x = ((torch.rand(512, 7, generator=g) * 2 - 1) * 2.0).to(DEV)
+    _, poses, cond = _inputs(512, 7)
+    cond = cond.to(DEV)
+    z, logdet = solver.nn_model(x, c=cond, rev=False)
+    x_back, _ = solver.nn_model(z, c=cond, rev=True)
+    assert (x_back - x).abs().max() < 5e-4
+    z_again, _ = solver.nn_model(x_back, c=cond, rev=False)
+    assert (z_again - z).abs().max() < 5e-4 * max(1.0, float(z.abs().max()))
+
+
+def test_forward_pass_needs_the_tcgen05_engine(monkeypatch):
+    monkeypatch.setenv("IKFLOW_B200_ENGINE", "mma")
+    hp = IkflowModelParameters()
+    hp.nb_nodes, hp.dim_latent_space = 2, 7
+    robot = ikflow_b200.Panda()
+    model = ikflow_b200.glow_cNF_model(hp, robot, 8, 7)
+    model.load_state_dict(make_synthetic_state_dict(hp, robot.actuated_joints_limits, seed=0))
+    _, poses, cond = _inputs(8, 7)
+    with pytest.raises(RuntimeError, match="tcgen05 engine only"):
+        model(torch.zeros(8, 7, device=DEV), c=cond.to(DEV), rev=False)

@@ -147,7 +147,7 @@ def test_nothing_computes_on_the_cpu():
         robot.forward_kinematics(torch.zeros(1, 7))
     with pytest.raises(RuntimeError, match="no CPU path"):
         robot.inverse_kinematics_step_levenburg_marquardt(torch.zeros(1, 7), torch.zeros(1, 7))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU path"):  # the forward (x -> z) direction has no CPU path either
         solver.nn_model(torch.zeros(4, 9), c=torch.zeros(4, 8), rev=False)
 
 
