@@ -43,8 +43,13 @@ def flow_case(name, nb_nodes, width, cfg, hidden, batch, robot):
     out32, _, inter = freia_flow.flow_inverse(sd, latent, cond, nb_nodes, cfg, hp.rnvp_clamp, return_intermediates=True)
     sd64 = freia_flow.state_dict_to(sd, torch.float64)
     out64, logdet64 = freia_flow.flow_inverse(sd64, latent.double(), cond.double(), nb_nodes, cfg, hp.rnvp_clamp)
+    # forward direction (x -> z with log-det, ikflow/training/lt_model.py:156) on joint-angle-like samples
+    fwd_x = (torch.rand(batch, width, generator=torch.Generator().manual_seed(99)) * 2 - 1) * 2.0
+    fz32, fld32 = freia_flow.flow_forward(sd, fwd_x, cond, nb_nodes, cfg, hp.rnvp_clamp)
+    fz64, fld64 = freia_flow.flow_forward(sd64, fwd_x.double(), cond.double(), nb_nodes, cfg, hp.rnvp_clamp)
     np.savez_compressed(
         os.path.join(OUT, f"flow_{name}.npz"),
+        fwd_x=fwd_x.numpy(), fwd_z_fp32=fz32.numpy(), fwd_z_fp64=fz64.numpy(), fwd_logdet_fp32=fld32.numpy(), fwd_logdet_fp64=fld64.numpy(),
         nb_nodes=nb_nodes, width=width, coeff_fn_config=cfg, hidden=hidden, rnvp_clamp=hp.rnvp_clamp,
         robot=robot.name, weights_sha256=sd_checksum(sd), latent=latent.numpy(), poses=poses.numpy(),
         out_fp32=out32.numpy(), out_fp64=out64.numpy(), logdet_fp64=logdet64.numpy(),

@@ -54,6 +54,11 @@ def test_golden_fixtures(name):
     assert (out.cpu().double() - torch.from_numpy(d["out_fp64"])).abs().max() < TOL
     first = solver.nn_model.inverse_blocks(latent, cond, hp.nb_nodes - 1, hp.nb_nodes - 1)
     assert (first.cpu() - torch.from_numpy(d["state_after_first_block_fp32"])).abs().max() < 2e-5
+    # forward direction of the same operator: nn_model(x, c=cond, rev=False) -> (z, log|det|)
+    z, ld = solver.nn_model(torch.from_numpy(d["fwd_x"]).to(DEV), c=cond, rev=False)
+    assert (z.cpu() - torch.from_numpy(d["fwd_z_fp32"])).abs().max() < TOL
+    assert (z.cpu().double() - torch.from_numpy(d["fwd_z_fp64"])).abs().max() < TOL
+    assert (ld.cpu().double() - torch.from_numpy(d["fwd_logdet_fp64"])).abs().max() < 1e-3
     assert solver.nn_model.status() == 0
 
 

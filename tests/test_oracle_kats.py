@@ -115,6 +115,16 @@ def test_oracle_reproduces_golden_flow_fixture(name):
     out, _ = freia_flow.flow_inverse(sd, latent[:n], cond[:n], hp.nb_nodes, hp.coeff_fn_config, float(d["rnvp_clamp"]))
     assert (out - torch.from_numpy(d["out_fp32"])[:n]).abs().max() < 2e-5  # BLAS blocking differs with the batch size
     assert (out.double() - torch.from_numpy(d["out_fp64"])[:n]).abs().max() < 5e-5
+    # forward direction (x -> z, log-det) of the same graph
+    x = torch.from_numpy(d["fwd_x"])
+    z, ld = freia_flow.flow_forward(sd, x[:n], cond[:n], hp.nb_nodes, hp.coeff_fn_config, float(d["rnvp_clamp"]))
+    assert (z - torch.from_numpy(d["fwd_z_fp32"])[:n]).abs().max() < 2e-5
+    assert (z.double() - torch.from_numpy(d["fwd_z_fp64"])[:n]).abs().max() < 5e-5
+    assert (ld.double() - torch.from_numpy(d["fwd_logdet_fp64"])[:n]).abs().max() < 1e-4
+    # ... and the reverse pass undoes it (the flow is a bijection)
+    back, ld_rev = freia_flow.flow_inverse(sd, z, cond[:n], hp.nb_nodes, hp.coeff_fn_config, float(d["rnvp_clamp"]))
+    assert (back - x[:n]).abs().max() < 1e-4
+    assert (ld_rev + ld).abs().max() < 1e-3
 
 
 def test_oracle_reproduces_golden_kinematics_fixture():
