@@ -146,6 +146,8 @@ def cpu_reference_arm(model_name: str, batch: int, steps: int, warmup: int, budg
     solver = OracleSolver(robot, sd, hp.nb_nodes, hp.dim_latent_space, hp.coeff_fn_config, hp.rnvp_clamp, device="cpu")
     _, poses = jk.sample_joint_angles_and_poses(jk.PANDA, batch, seed=1234)
     latent = torch.randn(batch, hp.dim_latent_space, generator=torch.Generator().manual_seed(4321))
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm is entitled to every host core
+    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
     cores = torch.get_num_threads()
     for _ in range(warmup):
         solver.generate_ik_solutions(poses, latent=latent)
