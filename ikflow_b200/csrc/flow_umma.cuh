@@ -385,9 +385,14 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
       }
     // the two groups take the chunks alternately: two chunks are always in the making, which hides the latency of
     // the (busy) shared memory
+    // cheap per-chunk stamps (IKFLOW_B200_DEBUG=4): row 4g+2 (group 0) / 4g+3... of the trace, SM clock
+    unsigned long long* tb = nullptr;
+    if (p.trace != nullptr && (p.debug & 4) && blockIdx.x < p.NT && g * 4 + 2 < p.trace_layers && j == 0 && lane == 0)
+      tb = p.trace + ((size_t)blockIdx.x * p.trace_layers + g * 4 + 2) * kTraceEvents + grp * 8;
     for (int i = grp; i < KCH; i += 2) {
       const int st = i % kStages;  // every layer starts at ring stage 0 (KCH % kStages == 0, checked at launch)
       const uint32_t stage_a = smem_u32(sm.ring[st]);
+      if (tb) tb[16 + (i >> 1)] = clock64();
       // 1. the chunk's first-layer weights have landed: pull them into registers ...
       mbar_wait(&sm.w1full[st], ((uint32_t)g * (uint32_t)(KCH / kStages) + (uint32_t)(i / kStages)) & 1u);
       uint64_t w[KB + 1][2];
@@ -395,9 +400,12 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
       // 2. ... while waiting for the tensor core to let go of the stage's activation area (previous use of the stage)
       const uint32_t use = ((uint32_t)g * (uint32_t)p.n_big * (uint32_t)KCH + (uint32_t)i) / kStages;
       if (use > 0) mbar_wait(&sm.empty[st], (use - 1) & 1);
+      if (tb) tb[32 + (i >> 1)] = clock64();
       if (!(p.debug & 2048)) jit_chunk_compute<KB, C::kAPlane>(stage_a, j, lane, xx, w);
+      if (tb) tb[48 + (i >> 1)] = clock64();
       if (!(p.debug & 1024)) fence_proxy_async_smem();  // generic-proxy writes -> the tensor core's (async proxy) reads
       bar_gen_group(grp);
+      if (tb) tb[64 + (i >> 1)] = clock64();
       if (j == 0 && lane == 0) {
         mbar_arrive(&sm.full[st]);
         mbar_arrive(&sm.w1empty[st]);

@@ -75,11 +75,13 @@ for cta in (0, 3):
             print("   issued " + " ".join(f"{int(v) - base:6d}" for v in sa[cta, layer, 48:64]))
 
 if os.environ.get('IKFLOW_B200_DEBUG') == '4':
-    print("just-in-time first layer, CTA 0 (cycles rel. to chunk 0 start): start / W1 landed / stage free / math+stores done / barrier passed")
-    for layer in (6, 10):
-        base = int(sa[0, layer, 16])
-        for nm, lo in (("start", 16), ("ready", 32)):
-            print(f"  layer {layer} {nm:>6s} " + " ".join(f"{int(v) - base:6d}" for v in sa[0, layer, lo:lo + 16]))
+    print("just-in-time first layer, CTA 0, SM-clock cycles relative to the MMA warp's first chunk of the layer; per group (0: epilogue warps -> even chunks, 1: helpers -> odd chunks): iteration start / waits passed / math+stores issued / fence+barrier passed")
+    for sub in (1, 2):
+        base = int(sa[0, 4 * sub, 16])  # MMA warp: chunk 0 landed
+        print(f"  subnet {sub}: MMA saw chunk i full at " + " ".join(f"{int(v) - base:6d}" for v in sa[0, 4 * sub, 16:32]))
+        for grp in (0, 1):
+            for nm, lo in (("start", 16), ("ready", 32), ("stored", 48), ("bar", 64)):
+                print(f"    group {grp} {nm:>7s} " + " ".join(f"{int(v) - base:6d}" for v in sa[0, 4 * sub + 2, lo + 8 * grp:lo + 8 * grp + 8]))
 
 # phase summary, averaged over subnets 1.. and the CTAs of the team
 import statistics as st
