@@ -33,7 +33,8 @@ def draw_latent(latent_distribution: str, latent_scale: float, shape: Tuple[int,
     assert latent_scale > 0
     assert len(shape) == 2
     if latent_distribution == "gaussian":
-        return latent_scale * torch.randn(shape, device=device)
+        z = torch.randn(shape, device=device)
+        return z if latent_scale == 1.0 else latent_scale * z  # x * 1.0 == x bit for bit: one launch less per call
     if latent_distribution == "uniform":
         return 2 * latent_scale * torch.rand(shape, device=device) - latent_scale
 
