@@ -257,6 +257,9 @@ __device__ __forceinline__ void bar_gen() { asm volatile("bar.sync 5, %0;" ::"n"
 __device__ __forceinline__ void bar_gen_group(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(6 + grp) : "memory"); }
 // the 128 threads of one epilogue group
 __device__ __forceinline__ void bar_group(int h) { asm volatile("bar.sync %0, 128;" ::"r"(3 + h) : "memory"); }
+__device__ __forceinline__ void stg64(void* p, uint32_t a, uint32_t b) {
+  asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
 __device__ __forceinline__ void stg128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -308,6 +311,51 @@ __device__ __forceinline__ void jit_chunk_compute(uint32_t stage_a, int j, int l
     const uint32_t off = tile_off_bytes(q + 8 * rr, f0);
     sts64u(stage_a + kWChunkU + off, hb[0], hb[1]);
     sts64u(stage_a + kWChunkU + APLANE + off, lb[0], lb[1]);
+  }
+}
+
+// Exchanged first layer (kernels without the just-in-time version), one tile of 32 rows x 16 features per call, same
+// lane mapping and arithmetic as the JIT loop (lane = row quad x feature quad, inputs in registers, one 128-bit weight
+// load per k and lane, packed fp32 FMAs in the original order): the head/tail halves go straight to the producer's slot
+// of the global scratch ring with 8-byte stores.  The thread-per-feature version it replaces spent most of its time on
+// broadcast 128-bit loads of the inputs (a quarter warp per bank phase): 7.2 us per subnet at 128 rows.
+template <int KB, int APLANE>
+__device__ __forceinline__ void first_layer_tile(uint32_t w_a, uint32_t b_a, const float (&x)[4][KB], int rb, int fb, int lane,
+                                                 uint8_t* dst_chunk0, int chunk_bytes) {
+  const int q = lane >> 2, fq = lane & 3;
+  const int f0 = fb * 16 + 4 * fq;  // feature inside the CTA's 128
+  uint64_t acc[4][2];
+  lds128_2x64(b_a + f0 * 4, acc[0][0], acc[0][1]);
+#pragma unroll
+  for (int rr = 1; rr < 4; ++rr) acc[rr][0] = acc[0][0], acc[rr][1] = acc[0][1];
+#pragma unroll
+  for (int k = 0; k < KB; ++k) {
+    uint64_t w01, w23;
+    lds128_2x64(w_a + (k * kFTU + f0) * 4, w01, w23);
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const uint64_t xk = pack2(x[rr][k], x[rr][k]);
+      acc[rr][0] = ffma2(xk, w01, acc[rr][0]);
+      acc[rr][1] = ffma2(xk, w23, acc[rr][1]);
+    }
+  }
+  uint8_t* dst = dst_chunk0 + (size_t)(f0 >> 6) * chunk_bytes;
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    uint32_t hb[2], lb[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float a0, a1;
+      unpack2(acc[rr][c], a0, a1);
+      a0 = leaky(a0), a1 = leaky(a1);
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
+      hb[c] = *reinterpret_cast<const uint32_t*>(&h2);
+      const __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - __uint_as_float(hb[c] << 16), a1 - __uint_as_float(hb[c] & 0xffff0000u));
+      lb[c] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    const uint32_t off = tile_off_bytes(rb * 32 + q + 8 * rr, f0 & 63);
+    stg64(dst + off, hb[0], hb[1]);
+    stg64(dst + APLANE + off, lb[0], lb[1]);
   }
 }
 
@@ -678,6 +726,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
     const uint32_t vt_a = smem_u32(sm.vt[h]);
     const int j8 = lane & 7;     // publish: row inside an 8-row block after the lane transpose
     const uint32_t xin_a = smem_u32(&sm.a[0][0]);
+    const bool tiled_first = !JIT && !(p.debug & 4096);
 
     // u <- u[:, table]
     auto permute_state = [&](const int* table) {
@@ -761,8 +810,31 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
             if (tid == 0) trace_ev(p, g * 4, 10);
             bar_gen<C::kGenThreads>();  // the helpers may read the subnet's input
             jit_layer_loop(0, warp, g, kin);
+          } else if (tiled_first) {
+            // ---- first layer, tile by tile, published as it is computed (first_layer_tile) ----
+            constexpr int kTilesPerWarp = (RT / 32) * (kFTU / 16) / C::kEpiWarps;
+            const int tile0 = warp * kTilesPerWarp;
+            const int rb = tile0 / (kFTU / 16), fb0 = tile0 % (kFTU / 16);
+            uint8_t* dst0 = act_slot + ((size_t)(axchg & 1) * NT + t) * kAStrideU;
+            auto run = [&](auto kb) {
+              constexpr int KB = decltype(kb)::value;
+              float x[4][KB];
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+                for (int k4 = 0; k4 < KB; k4 += 4) {
+                  const float4 xv = lds128(xin_a + ((rb * 32 + (lane >> 2) + 8 * rr) * kPad + k4) * 4);
+                  x[rr][k4] = xv.x, x[rr][k4 + 1] = xv.y, x[rr][k4 + 2] = xv.z, x[rr][k4 + 3] = xv.w;
+                }
+#pragma unroll
+              for (int ti = 0; ti < kTilesPerWarp; ++ti)
+                first_layer_tile<KB, C::kAPlane>(sp_a + (kSmFirstW - C::kSmShift) * 4, sp_a + (kSmFirstB - C::kSmShift) * 4, x, rb, fb0 + ti,
+                                                 lane, dst0, C::kAChunk);
+            };
+            if (kin <= 12) run(std::integral_constant<int, 12>{});
+            else run(std::integral_constant<int, kPad>{});
           } else {
-          // ---- first layer: fp32 FMA ----
+          // ---- first layer: fp32 FMA, one thread per feature (kept for A/B runs: IKFLOW_B200_DEBUG=4096) ----
             const float b0 = lds32(sp_a + (kSmFirstB - C::kSmShift + f) * 4);
 #pragma unroll
             for (int r = 0; r < ER; ++r) v[r] = b0;
@@ -826,6 +898,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
               const int buf = axchg & 1;
               uint8_t* dst = act_slot + ((size_t)buf * NT + t) * kAStrideU + (size_t)sub * C::kAChunk;
               const int kf8 = kf & ~7;
+              if (!(l == 0 && tiled_first))  // (the tiled first layer has stored its output already)
 #pragma unroll
               for (int r0 = 0; r0 < ER; r0 += 8) {
                 uint32_t wd[8];
