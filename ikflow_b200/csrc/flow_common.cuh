@@ -59,7 +59,11 @@ struct FlowParams {
   uint32_t epoch;       // sequence numbers of this launch start at epoch + 1
   unsigned long long* trace;  // debug: [cta < NT][layer][96] globaltimer stamps of team 0 (NULL = off)
   int trace_layers;
-  int debug;  // timing experiments only (IKFLOW_B200_DEBUG): results are garbage when non-zero
+  // timing experiments only (IKFLOW_B200_DEBUG, tcgen05 engine); results may be garbage when non-zero.  Bits: 1 / 2 skip
+  // the activation / weight copies, 4 per-chunk SM-clock stamps for the tracer, 32 / 64 / 128 / 256 L2 prefetch distance
+  // 0 / 1 / 3 / 4 layers (default 2), 1024 no proxy fence and 2048 no arithmetic in the just-in-time first layer,
+  // 4096 thread-per-feature instead of tiled exchanged first layer (valid results).
+  int debug;
   const float* in;
   const float* cond;
   float* out;

@@ -506,12 +506,8 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
       const int n2 = step_subnet(g2);
       const uint8_t* wnext =
           reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n2 * p.n_big + l2) * NT + t) * KCH * kWChunkU;
-      // ... plus, whatever the team, the first bytes of the chunks this CTA loads first (kc = 2t .. 2t+3): the address
-      // translation for the CTA's new 512 KB slice is then warm when the layer starts
-      for (int k = lane; k < KCH; k += 32) {
+      for (int k = lane; k < KCH; k += 32)
         if (k % p.slots == slot) bulk_prefetch_l2(wnext + (size_t)k * kWChunkU, kWChunkU);
-        else if ((p.debug & 8) && ((k - 2 * t) & (KCH - 1)) < 4) bulk_prefetch_l2(wnext + (size_t)k * kWChunkU, (p.debug & 16) ? kWChunkU : 128);
-      }
     };
     if (lw == 0) prefetch_small(0);
     bool gave_up = false;
@@ -563,13 +559,6 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
             bool ok = false;
             if (lane < NT && !((ready >> lane) & 1u)) ok = (int32_t)(ld_relaxed(my_flag) - expected) >= 0;
             ready |= __ballot_sync(0xffffffffu, ok);
-          }
-          if ((p.debug & 512) && !((ready >> c) & 1u)) {  // experiment: no weight copy in flight while the epilogue releases
-            while (!((ready >> c) & 1u)) {
-              bool ok = false;
-              if (lane < NT && !((ready >> lane) & 1u)) ok = (int32_t)(ld_relaxed(my_flag) - expected) >= 0;
-              ready |= __ballot_sync(0xffffffffu, ok);
-            }
           }
           const bool a_now = (ready >> c) & 1u;
           if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 64 + i);
