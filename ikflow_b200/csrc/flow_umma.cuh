@@ -554,25 +554,30 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
           }
           if (use > 0) mbar_wait_relaxed(&sm.empty[st], (use - 1) & 1);
           if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 32 + i);
+          // JIT kernel: the first two chunks of an exchanged layer (i = 0, 1 <-> kc = 2t, 2t+1) are this CTA's own output;
+          // its epilogue warps write them into the stage themselves (and arrive on the full barrier), so that the tensor
+          // core starts on them while the publish / fence / flag / poll round trip of the exchange is still under way
+          const bool own_chunk = JIT && !jit_layer && i < 2;
+          const bool skip_a = jit_layer || own_chunk;  // no activation copy by the loader
           // one look at the flags: if the producer is already done, weights and activations go out together
-          if (!((ready >> c) & 1u)) {
+          if (!skip_a && !((ready >> c) & 1u)) {
             bool ok = false;
             if (lane < NT && !((ready >> lane) & 1u)) ok = (int32_t)(ld_relaxed(my_flag) - expected) >= 0;
             ready |= __ballot_sync(0xffffffffu, ok);
           }
-          const bool a_now = (ready >> c) & 1u;
+          const bool a_now = !skip_a && ((ready >> c) & 1u);
           if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 64 + i);
           // No ordering is needed between lane 0's expect_tx and lane 1's copy: the phase cannot complete before the
           // (single) pending arrival, which is the expect_tx itself, whatever the transient sign of the tx-count.
           if (JIT) {
             // the full barrier of a stage takes two arrivals per phase: the weights' expect_tx, and the SIMT warps' "the
             // activations are written" in a JIT layer (a second plain arrival of the loader in the other layers)
-            if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], kWChunkU + (jit_layer ? 0 : C::kAChunk));
-            if (lane == 2 && !jit_layer) mbar_arrive(&sm.full[st]);
+            if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], kWChunkU + (skip_a ? 0 : C::kAChunk));
+            if (lane == 2 && !skip_a) mbar_arrive(&sm.full[st]);
           } else {
             if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], (p.debug & 1 ? 0 : C::kAChunk) + (p.debug & 2 ? 0 : kWChunkU));
           }
-          if (lane < ((a_now && !jit_layer) ? 2 : 1) && !((p.debug >> (1 - lane)) & 1)) bulk_g2s(my_dst, my_src, my_bytes, my_bar);
+          if (lane < (a_now ? 2 : 1) && !((p.debug >> (1 - lane)) & 1)) bulk_g2s(my_dst, my_src, my_bytes, my_bar);
           __syncwarp();
           if (!prefetched) {  // after this warp's first copies of the layer are on their way
             prefetched = true;
@@ -583,7 +588,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
           }
           if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 80 + i);
           if (lane == 0 && i == 0) trace_ev(p, g * 4 + l, 0);
-          if (!a_now) {
+          if (!a_now && !skip_a) {
             uint32_t spins = 0;
             long long t0 = 0;
             while (!((ready >> c) & 1u)) {
@@ -915,8 +920,22 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
                        __byte_perm(wd[4], wd[5], 0x5410), __byte_perm(wd[6], wd[7], 0x5410));
                 stg128(dst + C::kAPlane + off, __byte_perm(wd[0], wd[1], 0x7632), __byte_perm(wd[2], wd[3], 0x7632),
                        __byte_perm(wd[4], wd[5], 0x7632), __byte_perm(wd[6], wd[7], 0x7632));
+                if constexpr (JIT) {  // ... and into this CTA's own ring stages 0 / 1 (the next layer starts at stage 0)
+                  const uint32_t own_a = smem_u32(sm.ring[sub]) + kWChunkU + off;
+                  sts128u(own_a, __byte_perm(wd[0], wd[1], 0x5410), __byte_perm(wd[2], wd[3], 0x5410),
+                          __byte_perm(wd[4], wd[5], 0x5410), __byte_perm(wd[6], wd[7], 0x5410));
+                  sts128u(own_a + C::kAPlane, __byte_perm(wd[0], wd[1], 0x7632), __byte_perm(wd[2], wd[3], 0x7632),
+                          __byte_perm(wd[4], wd[5], 0x7632), __byte_perm(wd[6], wd[7], 0x7632));
+                }
               }
+              if constexpr (JIT) fence_proxy_async_smem();  // the tensor core reads the own chunks through the async proxy
               bar_epi<ET>();
+              if constexpr (JIT) {
+                if (tid == 0) {
+                  mbar_arrive(&sm.full[0]);
+                  mbar_arrive(&sm.full[1]);
+                }
+              }
               // st.release is cumulative over the stores the barrier ordered before it.  It is NOT optional: a relaxed
               // flag store lets consumers read stale chunks (scripts/stress_flow.py); its MEMBAR.GPU costs ~1 us.
               if (tid == 0) {
