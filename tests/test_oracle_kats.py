@@ -170,3 +170,23 @@ def test_oracle_exact_solver_last_valid_repeat_wins():
         ks = [k for k in range(3) if ok[k, p]]
         if ks:
             assert torch.equal(sol[p], q1[ks[-1] * 6 + p])
+
+
+def test_oracle_logdet_is_the_log_jacobian_determinant_of_its_own_forward_map():
+    """Internal consistency of the FrEIA restatement (it cannot be pinned against FrEIA itself, which is not installed):
+    the log-det returned by the forward pass equals log|det dz/dx| of that very map (autograd), and the reverse pass
+    returns its negative -- i.e. the coupling / clamp / permutation / fixed-linear formulas form a proper flow."""
+    hp, sd = _model(3, 7, 2, 64, jk.PANDA)
+    sd64 = freia_flow.state_dict_to(sd, torch.float64)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(4, 7, generator=g, dtype=torch.float64) * 2 - 1) * 2.0
+    _, poses = jk.sample_joint_angles_and_poses(jk.PANDA, 4, seed=3, dtype=torch.float64)
+    cond = torch.cat([poses, torch.zeros(4, 1, dtype=torch.float64)], dim=1)
+    z, logdet = freia_flow.flow_forward(sd64, x, cond, hp.nb_nodes, hp.coeff_fn_config, hp.rnvp_clamp)
+    for i in range(4):
+        f = lambda xi: freia_flow.flow_forward(sd64, xi[None], cond[i : i + 1], hp.nb_nodes, hp.coeff_fn_config, hp.rnvp_clamp)[0][0]
+        jac = torch.autograd.functional.jacobian(f, x[i])
+        assert abs(float(torch.linalg.slogdet(jac)[1]) - float(logdet[i])) < 1e-5  # logDetM of the state dict is an fp32 number
+    x_back, logdet_rev = freia_flow.flow_inverse(sd64, z, cond, hp.nb_nodes, hp.coeff_fn_config, hp.rnvp_clamp)
+    assert (x_back - x).abs().max() < 1e-10
+    assert (logdet_rev + logdet).abs().max() < 1e-10
