@@ -188,5 +188,5 @@ def test_oracle_logdet_is_the_log_jacobian_determinant_of_its_own_forward_map():
         jac = torch.autograd.functional.jacobian(f, x[i])
         assert abs(float(torch.linalg.slogdet(jac)[1]) - float(logdet[i])) < 1e-5  # logDetM of the state dict is an fp32 number
     x_back, logdet_rev = freia_flow.flow_inverse(sd64, z, cond, hp.nb_nodes, hp.coeff_fn_config, hp.rnvp_clamp)
-    assert (x_back - x).abs().max() < 1e-10
-    assert (logdet_rev + logdet).abs().max() < 1e-10
+    assert (x_back - x).abs().max() < 1e-6  # M and M_inv of the state dict are fp32 inverses of each other
+    assert (logdet_rev + logdet).abs().max() < 1e-6
