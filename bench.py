@@ -338,7 +338,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"], "traffic": 205_531_648 + 3_665_664 if args.model == "panda__full__lp191_5.25m" and B == 512 else None,
+                "frac": achieved / peaks["bf16_tflops"], "traffic": 205_474_816 + 6_067_456 if args.model == "panda__full__lp191_5.25m" and B == 512 else None,
                 "peak_source": peaks["source"] + ", burst bf16",
                 "kernel": "ikf::umma::flow_inverse_umma_kernel<%s>" % (("32, true" if width - width // 2 + 8 <= 12 else "32") if B <= 576 else "64" if B <= 1152 else "128"), "kernel_ms": kernel_ms,
                 "algorithmic_flops_per_launch": fl * B,
