@@ -10,6 +10,7 @@ first use like the reference does.  Two additions, both opt-in:
 """
 
 import os
+import sys
 import urllib.error
 from typing import Dict, Optional, Tuple
 from urllib.request import urlretrieve
@@ -110,7 +111,7 @@ def get_ik_solver(
     except (urllib.error.URLError, OSError) as e:
         if synthetic_seed is None:
             raise
-        print(f"get_ik_solver(): '{model_name}' weights unavailable ({e}); using synthetic weights, seed {synthetic_seed}")
+        print(f"get_ik_solver(): '{model_name}' weights unavailable ({e}); using synthetic weights, seed {synthetic_seed}", file=sys.stderr)
         ik_solver.load_state_dict_from_dict(
             make_synthetic_state_dict(hyper_parameters, robot.actuated_joints_limits, seed=synthetic_seed)
         )
