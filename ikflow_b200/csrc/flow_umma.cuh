@@ -251,8 +251,10 @@ __device__ __forceinline__ void sts128u(uint32_t a, uint32_t x, uint32_t y, uint
 template <int N>
 __device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 // epilogue + helper warps of the just-in-time first layer
+// (not inlined: the epilogue and the helper warps then arrive at ONE barrier instruction; compute-sanitizer's synccheck
+// reports two bar.sync sites on one barrier as divergence, although the hardware does not care)
 template <int N>
-__device__ __forceinline__ void bar_gen() { asm volatile("bar.sync 5, %0;" ::"n"(N) : "memory"); }
+__device__ __noinline__ void bar_gen() { asm volatile("bar.sync 5, %0;" ::"n"(N) : "memory"); }
 // the four warps of one generation group (0: epilogue warps, 1: helper warps)
 __device__ __forceinline__ void bar_gen_group(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(6 + grp) : "memory"); }
 // the 128 threads of one epilogue group
