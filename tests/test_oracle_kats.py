@@ -190,3 +190,44 @@ def test_oracle_logdet_is_the_log_jacobian_determinant_of_its_own_forward_map():
     x_back, logdet_rev = freia_flow.flow_inverse(sd64, z, cond, hp.nb_nodes, hp.coeff_fn_config, hp.rnvp_clamp)
     assert (x_back - x).abs().max() < 1e-6  # M and M_inv of the state dict are fp32 inverses of each other
     assert (logdet_rev + logdet).abs().max() < 1e-6
+
+
+# --- fixtures frozen from the reference's own code (scripts/make_golden_reference.py; oracle/ref_stub.py) -------------
+def test_oracle_reproduces_reference_approx_fixture():
+    """``reference_panda_approx.npz`` is the output of ``ikflow.ikflow_solver.IKFlowSolver.generate_ik_solutions`` run
+    from /root/reference; the oracle must give the same numbers wherever this suite runs."""
+    d = np.load(os.path.join(GOLD, "reference_panda_approx.npz"))
+    hp, sd = _model(12, 7, 3, 1024)
+    solver = OracleSolver(jk.PANDA, sd, 12, 7, 3)
+    poses = torch.from_numpy(d["poses"])
+    n = 64
+    for tag in ("s100", "s075"):
+        latent = torch.from_numpy(d[f"latent_{tag}"])
+        got = solver.generate_ik_solutions(poses[:n], latent=latent[:n])
+        assert (got - torch.from_numpy(d[f"q_{tag}"])[:n]).abs().max() < 2e-5  # BLAS blocking differs with the batch size
+        raw = solver.generate_ik_solutions(poses[:n], latent=latent[:n], clamp_to_joint_limits=False)
+        assert (raw - torch.from_numpy(d[f"q_unclamped_{tag}"])[:n]).abs().max() < 2e-5
+    lat1 = torch.from_numpy(d["single_pose_latent"])
+    assert (solver.generate_ik_solutions(poses[5], 33, latent=lat1) - torch.from_numpy(d["single_pose_q"])).abs().max() < 2e-5
+
+
+def test_oracle_reproduces_reference_exact_fixture_scenario_b():
+    """BASELINE config 3 sizes (n = 2048, repeat_counts (1, 3, 10)) with trained-like seeds: the oracle's restatement of
+    ikflow_solver.py:119-247 / :345-411 must reproduce the reference's own output bit for bit."""
+    from oracle.scenarios import PseudoFlow, seeded_draws
+
+    d = np.load(os.path.join(GOLD, "reference_panda_exact_n2048.npz"))
+    poses, q_true = torch.from_numpy(d["poses"]), torch.from_numpy(d["q_true"])
+    hp, sd = _model(1, 7, 1, 32)
+    draw, log = seeded_draws(int(d["draw_seed0"]))
+    solver = OracleSolver(jk.PANDA, sd, 1, 7, 1, latent_source=lambda shape, dev: draw("gaussian", 1.0, shape, dev))
+    flow = PseudoFlow(poses, q_true, float(d["sigma_b"]))
+    solver._run_inference = lambda latent, cond, clamp: jk.clamp_to_joint_limits(jk.PANDA, flow(latent, c=cond)[0])
+    sols, valids = solver.generate_exact_ik_solutions(
+        poses, tuple(int(r) for r in d["repeat_counts"]), float(d["pos_thr"]), float(d["rot_thr"]), run_lma_on_cpu=False
+    )
+    assert [list(s) for s, _ in log] == d["b_draw_shapes"].tolist()
+    assert [h for _, h in log] == d["b_draw_sha256"].tolist()  # torch's CPU generator still produces the frozen stream
+    assert torch.equal(valids, torch.from_numpy(d["b_valids"]))
+    assert torch.equal(sols, torch.from_numpy(d["b_solutions"]))
+    assert int(valids.sum()) == 1966 and len(log) == 3 and log[2][0][0] % 10 == 0  # the r = 10 pass ran
