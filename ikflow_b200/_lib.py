@@ -12,10 +12,12 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64
 LIB_PATH = os.environ.get("IKFLOW_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libikflow_b200.so")
 
 IKF_OK = 0
+IKF_ESTATUS = -5
 IKF_STATUS_NONFINITE = 1
 IKF_STATUS_SYNC_TIMEOUT = 2
 IKF_PRECISION_BF16X3 = 0
 IKF_PRECISION_BF16X1 = 1
+IKF_PRECISION_FP16X3 = 2
 IKF_MAX_WIDTH = 16
 IKF_MAX_LINKS = 16
 IKF_MAX_DOF = 8
@@ -39,18 +41,20 @@ PROTOTYPES = {
     "ikf_flow_create": (c_int, [POINTER(IkfFlowDesc), c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(c_void_p)]),
     "ikf_flow_destroy": (None, [c_void_p]),
     "ikf_flow_weight_count": (c_size_t, [POINTER(IkfFlowDesc)]),
-    "ikf_flow_reserve": (c_int, [c_void_p, c_int]),
     "ikf_flow_inverse": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ikf_flow_inverse_blocks": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ikf_flow_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "ikf_flow_set_forward_tables": (c_int, [c_void_p, c_void_p, c_float]),
     "ikf_flow_status": (c_int, [c_void_p, c_void_p, POINTER(c_uint32)]),
+    "ikf_flow_poll_status": (c_int, [c_void_p, POINTER(c_uint32)]),
+    "ikf_flow_last_kernel": (c_char_p, [c_void_p]),
     "ikf_flow_debug_trace": (c_int, [c_void_p, c_void_p, c_int]),
     "ikf_flow_info": (c_int, [c_void_p, POINTER(c_size_t), POINTER(c_int), POINTER(c_int)]),
     "ikf_robot_create": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(c_void_p)]),
     "ikf_robot_destroy": (None, [c_void_p]),
     "ikf_robot_ndof": (c_int, [c_void_p]),
     "ikf_forward_kinematics": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "ikf_sample_joint_angles_and_poses": (c_int, [c_void_p, c_uint64, c_uint64, c_double, c_void_p, c_void_p, c_int, c_void_p]),
     "ikf_clamp_to_joint_limits": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "ikf_lm_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p]),
     "ikf_pose_error": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),

@@ -26,6 +26,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -46,6 +47,9 @@ static inline uint16_t bf16_bits_rn(float f) {
   x += 0x7fffu + lsb;
   return (uint16_t)(x >> 16);
 }
+// fp16 (round to nearest even; overflow -> inf) through the host half of cuda_fp16.h
+static inline uint16_t fp16_bits_rn(float f) { return __half_as_ushort(__float2half_rn(f)); }
+static inline float fp16_bits_to_float(uint16_t b) { return __half2float(__ushort_as_half(b)); }
 static inline float bf16_bits_to_float(uint16_t b) {
   uint32_t x = (uint32_t)b << 16;
   float f;
@@ -61,7 +65,7 @@ static bool desc_ok(const IkfFlowDesc* d) {
   if (d->coeff_fn_config < 1 || d->coeff_fn_config > 4) return false;
   if (d->hidden < 64 || d->hidden % 64 != 0 || d->hidden > 2048) return false;
   if (d->ndof < 1 || d->ndof > d->ndim_tot) return false;
-  if (d->precision != IKF_PRECISION_BF16X3 && d->precision != IKF_PRECISION_BF16X1) return false;
+  if (d->precision != IKF_PRECISION_BF16X3 && d->precision != IKF_PRECISION_BF16X1 && d->precision != IKF_PRECISION_FP16X3) return false;
   const int s1 = d->ndim_tot / 2, s2 = d->ndim_tot - s1;
   if (s2 + d->dim_cond > kPad || 2 * s2 > kPad) return false;
   return true;
@@ -96,6 +100,29 @@ struct IkfFlow {
   unsigned long long* trace = nullptr;
   int trace_layers = 0;
   size_t smem_bytes = 0;
+  // One handle owns ONE exchange workspace (activation ring, partial sums, flags) and one sequence-number space, and a
+  // launch occupies every SM (cooperative), so launches of a handle cannot overlap anyway: `mu` serialises the host
+  // side (epoch, parameters), `done` / `last_stream` order a launch after the previous one when it comes from another
+  // stream.  Any number of host threads and streams may therefore share a handle.
+  std::mutex mu;
+  cudaEvent_t done = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool has_last = false;
+  // developer switches, read ONCE when the handle is created (IKFLOW_B200_RT / _DEBUG)
+  int forced_rt = 0;
+  int debug = 0;
+  // Mirror of the device status word in mapped host memory, written by the kernel itself when it gives up on a wait:
+  // [0] status bits, [1] id of the aborted launch.  Read without any synchronisation by the next call on the handle.
+  volatile uint32_t* status_host = nullptr;
+  const char* last_kernel = "";
+  // the kernels of this handle (engine, operand format): [0] 32-row groups, [1] 64, [2] 128 (tcgen05 only), [3] 32 with
+  // the just-in-time first layer (tcgen05 only)
+  struct Kernel {
+    const void* fn = nullptr;
+    int threads = 0;
+    size_t smem = 0;
+    const char* name = "";
+  } kern[4];
 };
 
 using namespace ikf;
@@ -111,9 +138,14 @@ size_t ikf_flow_weight_count(const IkfFlowDesc* desc) {
 
 void ikf_flow_destroy(IkfFlow* flow) {
   if (!flow) return;
-  if (flow->blob) {
+  {
     DeviceGuard guard(flow->device);
-    cudaFree(flow->blob);
+    if (flow->done) {
+      if (flow->has_last) cudaEventSynchronize(flow->done);  // the workspace must outlive the last launch
+      cudaEventDestroy(flow->done);
+    }
+    if (flow->blob) cudaFree(flow->blob);
+    if (flow->status_host) cudaFreeHost((void*)flow->status_host);
   }
   delete flow;
 }
@@ -165,6 +197,16 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
     }
   }
   f->engine = engine;
+  const bool f16 = desc->precision == IKF_PRECISION_FP16X3;
+  if (f16 && !engine) {
+    delete f;
+    return fail(IKF_EINVAL, "ikf_flow_create: IKF_PRECISION_FP16X3 is implemented by the tcgen05 engine only (hidden %% 128 == 0, hidden <= 1024, coeff_fn_config >= 2)");
+  }
+  if (const char* env = std::getenv("IKFLOW_B200_RT")) {  // debugging / A-B comparisons
+    const int v = std::atoi(env);
+    if (v == 32 || v == 64 || (v == 128 && engine)) f->forced_rt = v;
+  }
+  if (const char* env = std::getenv("IKFLOW_B200_DEBUG")) f->debug = std::atoi(env);
   const int FT = engine ? umma::kFTU : kFT;  // hidden features per CTA
   const int NT = H / FT;                     // CTAs per team
   const int KCH = H / kKC;                   // 64-wide k-chunks per hidden layer
@@ -214,9 +256,15 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
               const float* src = w + (size_t)(tt * FT + r) * H + c * kKC;
               for (int e = 0; e < kKC; ++e) {
                 const uint32_t off = tile_off_bytes(r, e) / 2;
-                const uint16_t hb = bf16_bits_rn(src[e]);
-                hi[off] = hb;
-                lo[off] = bf16_bits_rn(src[e] - bf16_bits_to_float(hb));
+                if (f16) {  // scaled tails, see umma::kTailScaleF16
+                  const uint16_t hb = fp16_bits_rn(src[e]);
+                  hi[off] = hb;
+                  lo[off] = fp16_bits_rn((src[e] - fp16_bits_to_float(hb)) * umma::kTailScaleF16);
+                } else {
+                  const uint16_t hb = bf16_bits_rn(src[e]);
+                  hi[off] = hb;
+                  lo[off] = bf16_bits_rn(src[e] - bf16_bits_to_float(hb));
+                }
               }
             }
           }
@@ -341,6 +389,19 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
     delete f;
     return fail(IKF_ENOMEM, "ikf_flow_create: cudaMalloc(%zu) failed: %s", f->blob_bytes, cudaGetErrorString(e));
   }
+  {
+    void* hs = nullptr;
+    e = cudaHostAlloc(&hs, 4 * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e == cudaSuccess) {
+      std::memset(hs, 0, 4 * sizeof(uint32_t));
+      f->status_host = (volatile uint32_t*)hs;
+      e = cudaEventCreateWithFlags(&f->done, cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+      ikf_flow_destroy(f);
+      return fail(IKF_ECUDA, "ikf_flow_create: host status / event setup failed: %s", cudaGetErrorString(e));
+    }
+  }
   uint8_t* base = (uint8_t*)f->blob;
   e = cudaMemset(base + off_act, 0, f->blob_bytes - off_act);
   if (e == cudaSuccess && big_elems) e = cudaMemcpy(base + off_big, big.data(), big_elems * 2, cudaMemcpyHostToDevice);
@@ -363,33 +424,37 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
     f->smem64 = sizeof(FlowSmem<64>) + 1024;
   }
   f->smem_bytes = f->smem64;
-  const void* k32 = engine ? (const void*)umma::flow_inverse_umma_kernel<32> : (const void*)flow_inverse_kernel<32>;
-  const void* k64 = engine ? (const void*)umma::flow_inverse_umma_kernel<64> : (const void*)flow_inverse_kernel<64>;
-  const int threads32 = engine ? umma::Cfg<32>::kThreads : kThreads;
-  const int threads64 = engine ? umma::Cfg<64>::kThreads : kThreads;
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem32);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem64);
-  if (e == cudaSuccess && engine)
-    e = cudaFuncSetAttribute(umma::flow_inverse_umma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem128);
-  if (e == cudaSuccess && engine && f->jit)
-    e = cudaFuncSetAttribute(umma::flow_inverse_umma_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f->smem32j);
-  if (e == cudaSuccess) {
+  if (engine && f16) {
+    f->kern[0] = {(const void*)umma::flow_inverse_umma_kernel<32, false, true>, umma::Cfg<32>::kThreads, f->smem32, "ikf::umma::flow_inverse_umma_kernel<32,false,true>"};
+    f->kern[1] = {(const void*)umma::flow_inverse_umma_kernel<64, false, true>, umma::Cfg<64>::kThreads, f->smem64, "ikf::umma::flow_inverse_umma_kernel<64,false,true>"};
+    f->kern[2] = {(const void*)umma::flow_inverse_umma_kernel<128, false, true>, umma::Cfg<128>::kThreads, f->smem128, "ikf::umma::flow_inverse_umma_kernel<128,false,true>"};
+    f->kern[3] = {(const void*)umma::flow_inverse_umma_kernel<32, true, true>, umma::Cfg<32, true>::kThreads, f->smem32j, "ikf::umma::flow_inverse_umma_kernel<32,true,true>"};
+  } else if (engine) {
+    f->kern[0] = {(const void*)umma::flow_inverse_umma_kernel<32>, umma::Cfg<32>::kThreads, f->smem32, "ikf::umma::flow_inverse_umma_kernel<32,false,false>"};
+    f->kern[1] = {(const void*)umma::flow_inverse_umma_kernel<64>, umma::Cfg<64>::kThreads, f->smem64, "ikf::umma::flow_inverse_umma_kernel<64,false,false>"};
+    f->kern[2] = {(const void*)umma::flow_inverse_umma_kernel<128>, umma::Cfg<128>::kThreads, f->smem128, "ikf::umma::flow_inverse_umma_kernel<128,false,false>"};
+    f->kern[3] = {(const void*)umma::flow_inverse_umma_kernel<32, true>, umma::Cfg<32, true>::kThreads, f->smem32j, "ikf::umma::flow_inverse_umma_kernel<32,true,false>"};
+  } else {
+    f->kern[0] = {(const void*)flow_inverse_kernel<32>, kThreads, f->smem32, "ikf::flow_inverse_kernel<32>"};
+    f->kern[1] = {(const void*)flow_inverse_kernel<64>, kThreads, f->smem64, "ikf::flow_inverse_kernel<64>"};
+  }
+  if (!f->jit) f->kern[3] = IkfFlow::Kernel();
+  {
     // the teams spin on each other's flags, so every CTA of a launch must be resident: size the slot count from
     // what the device really fits
-    int occ32 = 0, occ64 = 0, occ128 = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, k32, threads32, f->smem32);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, k64, threads64, f->smem64);
-    if (e == cudaSuccess && engine)
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ128, umma::flow_inverse_umma_kernel<128>, umma::Cfg<128>::kThreads, f->smem128);
-    int occ32j = 1;
-    if (e == cudaSuccess && engine && f->jit)
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32j, umma::flow_inverse_umma_kernel<32, true>, umma::Cfg<32, true>::kThreads, f->smem32j);
-    const int occ = std::min(std::min(std::min(occ32, occ64), occ128), occ32j);
+    int occ = ctas_per_sm;
+    for (const IkfFlow::Kernel& k : f->kern) {
+      if (!k.fn || e != cudaSuccess) continue;
+      e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem);
+      int o = 0;
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k.fn, k.threads, k.smem);
+      occ = std::min(occ, o);
+    }
     if (e == cudaSuccess && occ < 1) {
       ikf_flow_destroy(f);
       return fail(IKF_EDEVICE, "ikf_flow_create: the flow kernel does not fit on an SM of device %d", device);
     }
-    f->slots_max = std::max(1, std::min(occ, ctas_per_sm) * f->num_sms / NT);
+    f->slots_max = std::max(1, occ * f->num_sms / NT);
   }
   if (e != cudaSuccess) {
     ikf_flow_destroy(f);
@@ -417,13 +482,17 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   p.act_flag = (uint32_t*)(base + off_flags);
   p.part_flag = p.act_flag + (size_t)slots * 2 * NT;
   p.status = p.part_flag + (size_t)slots * 2 * NT;
+  {
+    void* dev_view = nullptr;
+    e = cudaHostGetDevicePointer(&dev_view, (void*)f->status_host, 0);
+    if (e != cudaSuccess) {
+      ikf_flow_destroy(f);
+      return fail(IKF_ECUDA, "ikf_flow_create: cudaHostGetDevicePointer failed: %s", cudaGetErrorString(e));
+    }
+    p.status_host = (uint32_t*)dev_view;
+  }
   *out = f;
   return IKF_OK;
-}
-
-int ikf_flow_reserve(IkfFlow* flow, int max_batch) {
-  if (!flow || max_batch < 0) return fail(IKF_EINVAL, "ikf_flow_reserve: bad arguments");
-  return IKF_OK;  // the workspace is per team, not per row: nothing grows with the batch
 }
 
 static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* cond, int cond_ld, int cond_rows,
@@ -443,6 +512,16 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
     return fail(IKF_EINVAL, "%s: bad block range [%d..%d] for %d blocks", name, block_first, block_last, d.nb_nodes);
   DeviceGuard guard(flow->device);
   if (!guard.ok) return fail(IKF_ECUDA, "%s: cudaSetDevice(%d) failed", name, flow->device);
+  std::lock_guard<std::mutex> lock(flow->mu);
+  // A previous launch that gave up on an inter-CTA wait has written into the mapped status word by now (or will have
+  // by the time its stream is synchronised): refuse to build on its garbage.  No synchronisation: a plain host read.
+  if (flow->status_host[0] & IKF_STATUS_SYNC_TIMEOUT) {
+    const uint32_t id = flow->status_host[1];
+    flow->status_host[0] &= ~IKF_STATUS_SYNC_TIMEOUT;
+    return fail(IKF_ESTATUS, "%s: an earlier launch on this handle (id %u) timed out waiting for another CTA "
+                "(IKF_STATUS_SYNC_TIMEOUT): its output is invalid.  The usual cause is a kernel of another process or "
+                "stream holding SMs, so that the cooperative launch could not make progress", name, id);
+  }
 
   FlowParams p = flow->base;
   p.in = in; p.in_ld = in_ld; p.cond = cond; p.cond_ld = cond_ld; p.cond_rows = cond_rows; p.cond_cols = cond_cols;
@@ -455,16 +534,13 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   int rt = ((batch + 31) / 32 <= flow->slots_max) ? 32 : 64;
   // umma engine: 128-row groups once 64-row groups would need more than one wave (twice the rows per weight byte)
   if (flow->engine && (batch + 63) / 64 > flow->slots_max) rt = 128;
-  if (const char* env = std::getenv("IKFLOW_B200_RT")) {  // debugging / A-B comparisons
-    const int v = std::atoi(env);
-    if (v == 32 || v == 64 || (v == 128 && flow->engine)) rt = v;
-  }
+  if (flow->forced_rt) rt = flow->forced_rt;
   p.n_rowgroups = (batch + rt - 1) / rt;
   p.slots = std::min(p.n_rowgroups, flow->slots_max);
   p.epoch = flow->epoch;
   p.trace = flow->trace;
   p.trace_layers = flow->trace_layers;
-  if (const char* env = std::getenv("IKFLOW_B200_DEBUG")) p.debug = std::atoi(env);
+  p.debug = flow->debug;
   // every flag of this launch stays below epoch + 1 + (row groups per slot) * (subnets) * (exchanges per subnet)
   const uint32_t rg_per_slot = (uint32_t)((p.n_rowgroups + p.slots - 1) / p.slots);
   flow->epoch += rg_per_slot * 2u * (uint32_t)(block_first - block_last + 1) * (uint32_t)(flow->n_big + 1) + 2u;
@@ -474,24 +550,29 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   void* args[] = {(void*)&p};
   // cooperative launch = the driver guarantees that all CTAs of all teams are co-resident (the teams spin on each
   // other's flags)
-  const void* fn;
-  int threads;
-  size_t smem;
-  if (flow->engine) {
-    const bool jit = rt == 32 && flow->jit;
-    fn = jit ? (const void*)umma::flow_inverse_umma_kernel<32, true>
-             : rt == 32 ? (const void*)umma::flow_inverse_umma_kernel<32>
-                        : rt == 64 ? (const void*)umma::flow_inverse_umma_kernel<64> : (const void*)umma::flow_inverse_umma_kernel<128>;
-    threads = jit ? umma::Cfg<32, true>::kThreads : rt == 32 ? umma::Cfg<32>::kThreads : rt == 64 ? umma::Cfg<64>::kThreads : umma::Cfg<128>::kThreads;
-    smem = jit ? flow->smem32j : rt == 32 ? flow->smem32 : rt == 64 ? flow->smem64 : flow->smem128;
-  } else {
-    fn = rt == 32 ? (const void*)flow_inverse_kernel<32> : (const void*)flow_inverse_kernel<64>;
-    threads = kThreads;
-    smem = rt == 32 ? flow->smem32 : flow->smem64;
+  const IkfFlow::Kernel& k = flow->kern[(rt == 32 && flow->jit) ? 3 : rt == 32 ? 0 : rt == 64 ? 1 : 2];
+  const void* fn = k.fn;
+  const int threads = k.threads;
+  const size_t smem = k.smem;
+  flow->last_kernel = k.name;
+  flow->smem_bytes = smem;
+  // stream-ordered reuse of the workspace: a launch from another stream waits for the previous launch of this handle
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &capturing);
+  if (flow->has_last && flow->last_stream != st && capturing == cudaStreamCaptureStatusNone) {
+    cudaError_t we = cudaStreamWaitEvent(st, flow->done, 0);
+    if (we != cudaSuccess) return fail(IKF_ECUDA, "%s: cudaStreamWaitEvent failed: %s", name, cudaGetErrorString(we));
   }
-  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, (cudaStream_t)stream);
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, st);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return fail(IKF_ECUDA, "%s: launch failed: %s", name, cudaGetErrorString(e));
+  if (capturing == cudaStreamCaptureStatusNone) {
+    e = cudaEventRecord(flow->done, st);
+    if (e != cudaSuccess) return fail(IKF_ECUDA, "%s: cudaEventRecord failed: %s", name, cudaGetErrorString(e));
+    flow->last_stream = st;
+    flow->has_last = true;
+  }  // (inside a stream capture the graph owns the ordering: use one capturing stream per handle)
   return IKF_OK;
 }
 
@@ -534,11 +615,19 @@ int ikf_flow_status(IkfFlow* flow, void* stream, uint32_t* status_out) {
   if (!flow || !status_out) return fail(IKF_EINVAL, "ikf_flow_status: bad arguments");
   DeviceGuard guard(flow->device);
   if (!guard.ok) return fail(IKF_ECUDA, "ikf_flow_status: cudaSetDevice(%d) failed", flow->device);
+  std::lock_guard<std::mutex> lock(flow->mu);
   uint32_t host[2] = {0, 0};
   IKF_CUDA(cudaMemcpyAsync(host, flow->base.status, sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   IKF_CUDA(cudaMemsetAsync(flow->base.status, 0, sizeof(uint32_t), (cudaStream_t)stream));
   IKF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-  *status_out = host[0];
+  *status_out = host[0] | flow->status_host[0];
+  flow->status_host[0] = 0;
+  return IKF_OK;
+}
+
+int ikf_flow_poll_status(IkfFlow* flow, uint32_t* status_out) {
+  if (!flow || !status_out) return fail(IKF_EINVAL, "ikf_flow_poll_status: bad arguments");
+  *status_out = flow->status_host[0];  // mapped host memory, written by the kernels: no synchronisation
   return IKF_OK;
 }
 
@@ -548,6 +637,8 @@ int ikf_flow_debug_trace(IkfFlow* flow, unsigned long long* dev_stamps, int n_la
   flow->trace_layers = n_layers;
   return IKF_OK;
 }
+
+const char* ikf_flow_last_kernel(IkfFlow* flow) { return flow ? flow->last_kernel : ""; }
 
 int ikf_flow_info(IkfFlow* flow, size_t* packed_weight_bytes, int* grid_ctas_last, int* smem_bytes) {
   if (!flow) return fail(IKF_EINVAL, "ikf_flow_info: flow is NULL");

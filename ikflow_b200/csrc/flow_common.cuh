@@ -56,6 +56,7 @@ struct FlowParams {
   uint32_t* act_flag;   // [slot][2][NT]
   uint32_t* part_flag;  // [slot][2][NT]
   uint32_t* status;     // [0] status bits, [1] id of the launch that aborted
+  uint32_t* status_host;  // the same two words in mapped host memory: the host reads them without synchronising
   uint32_t epoch;       // sequence numbers of this launch start at epoch + 1
   unsigned long long* trace;  // debug: [cta < NT][layer][96] globaltimer stamps of team 0 (NULL = off)
   int trace_layers;
@@ -179,10 +180,31 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// A wait gave up: mark the launch as aborted for every other waiter, on the device and (plain stores, mapped memory)
+// for the host, which checks the word at the next call on the handle without any synchronisation.
+__device__ __forceinline__ void report_timeout(uint32_t* status, uint32_t* status_host, uint32_t launch_id) {
+  atomicOr(status, IKF_STATUS_SYNC_TIMEOUT);
+  atomicExch(status + 1, launch_id);
+  if (status_host != nullptr) {
+    volatile uint32_t* h = status_host;
+    h[1] = launch_id;
+    h[0] = h[0] | IKF_STATUS_SYNC_TIMEOUT;
+    __threadfence_system();
+  }
+}
+__device__ __forceinline__ void report_nonfinite(uint32_t* status, uint32_t* status_host) {
+  atomicOr(status, IKF_STATUS_NONFINITE);
+  if (status_host != nullptr) {
+    volatile uint32_t* h = status_host;
+    h[0] = h[0] | IKF_STATUS_NONFINITE;
+  }
+}
+
 // Wait until *flag has reached `expected` (wrap-safe).  Gives up (and makes every later wait of this launch give up)
 // after about a second: the results are then garbage and IKF_STATUS_SYNC_TIMEOUT is reported, but the GPU is not hung.
 // The caller issues the acquire fence.
-__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t expected, uint32_t* status, uint32_t launch_id) {
+__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t expected, uint32_t* status, uint32_t launch_id,
+                                          uint32_t* status_host = nullptr) {
   uint32_t spins = 0;
   long long t0 = 0;
   while (true) {
@@ -194,8 +216,7 @@ __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t expecte
       if ((spins & 255u) == 0) {
         if (ld_relaxed(status + 1) == launch_id) return;
         if (clock64() - t0 > 2500000000LL) {
-          atomicOr(status, IKF_STATUS_SYNC_TIMEOUT);
-          atomicExch(status + 1, launch_id);
+          report_timeout(status, status_host, launch_id);
           return;
         }
       }

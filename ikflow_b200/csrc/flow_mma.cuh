@@ -217,8 +217,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) flow_inverse_kernel(cons
                 if (lane == 0) {
                   if (ld_relaxed(p.status + 1) == launch_id) bail = 1;
                   else if (clock64() - t0 > 2500000000LL) {
-                    atomicOr(p.status, IKF_STATUS_SYNC_TIMEOUT);
-                    atomicExch(p.status + 1, launch_id);
+                    report_timeout(p.status, p.status_host, launch_id);
                     bail = 1;
                   }
                 }
@@ -503,7 +502,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) flow_inverse_kernel(cons
           const uint32_t pexp = p.epoch + 1 + part_w[pb];
           if (tid == 0) st_release(pflag + pb * NT + t, pexp);  // cumulative over the barrier: one fence per CTA
           if (warp == 0) {
-            for (int c = lane; c < NT; c += 32) wait_flag(pflag + pb * NT + c, pexp, p.status, launch_id);
+            for (int c = lane; c < NT; c += 32) wait_flag(pflag + pb * NT + c, pexp, p.status, launch_id, p.status_host);
             __threadfence();  // acquire
           }
           bar_compute();
@@ -568,11 +567,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) flow_inverse_kernel(cons
             // FixedLinearTransform reverse (x - b) @ M_inv, slice, joint-limit clamp (ikflow_solver.py:98-102)
             o = 0.f;
             for (int k = 0; k < p.W; ++k) o = fmaf(sm.u[r][k] - p.flt_b[k], p.m_inv[k * kPad + j], o);
-            if (p.clamp_out && j < p.ndof) o = fminf(fmaxf(o, p.lo[j]), p.hi[j]);
+            // NaN / inf are reported BEFORE the clamp, and NaN survives it as in torch.clamp
+            if (!isfinite(o)) report_nonfinite(p.status, p.status_host);
+            if (p.clamp_out && j < p.ndof && o == o) o = fminf(fmaxf(o, p.lo[j]), p.hi[j]);
           } else {
             o = sm.u[r][j];
+            if (!isfinite(o)) report_nonfinite(p.status, p.status_host);
           }
-          if (!isfinite(o)) atomicOr(p.status, IKF_STATUS_NONFINITE);
           p.out[(size_t)row * p.out_ld + j] = o;
         }
       }

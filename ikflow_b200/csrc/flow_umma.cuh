@@ -13,6 +13,8 @@
 // Requires hidden % 128 == 0 and hidden <= 1024.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include <type_traits>
 
 #include "flow_common.cuh"
@@ -55,6 +57,46 @@ constexpr int kJitMaxK = 12;                       // widest first-layer input (
 constexpr int kJitChunkFloats = kPad * kKC + kKC;  // 1088
 constexpr int kJitChunkBytes = kJitChunkFloats * 4;  // 4352
 static_assert(kJitChunkBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+// Operand formats of the hidden-layer products (IkfFlowDesc.precision).  Both split every fp32 operand x into a 16-bit
+// head and tail and issue head*head + head*tail + tail*head with fp32 accumulation:
+//   bf16x3  tail = bf16(x - head): 16 mantissa bits, the exponent range of fp32 (nothing can overflow or underflow)
+//   fp16x3  tail = fp16((x - head) * 2^11): 22 mantissa bits -- as close to the fp32 reference as fp32 is to fp64 -- at
+//           the price of fp16's range: |x| must stay below 65504 (hidden activations of a trained network are O(1);
+//           beyond it the head is inf, the outputs NaN and IKF_STATUS_NONFINITE is raised).  The scaled tails make the two
+//           correction products 2^11 too large, so they get their own accumulator (the second half of the TMEM tile,
+//           which the stacked head|tail activation operand fills anyway) and the epilogue adds main + corr * 2^-11.
+constexpr float kTailScaleF16 = 2048.f;
+
+// (a0, a1) -> packed heads (a0 in the low half) and packed tails
+template <bool F16>
+__device__ __forceinline__ void split_pair(float a0, float a1, uint32_t& hb, uint32_t& lb) {
+  if constexpr (F16) {
+    const __half2 h2 = __floats2half2_rn(a0, a1);
+    hb = *reinterpret_cast<const uint32_t*>(&h2);
+    const float2 hf = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn((a0 - hf.x) * kTailScaleF16, (a1 - hf.y) * kTailScaleF16);
+    lb = *reinterpret_cast<const uint32_t*>(&l2);
+  } else {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);  // .x = a0 (low half), one instruction
+    hb = *reinterpret_cast<const uint32_t*>(&h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - __uint_as_float(hb << 16), a1 - __uint_as_float(hb & 0xffff0000u));
+    lb = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+}
+// one value -> head in the low half, tail in the high half
+template <bool F16>
+__device__ __forceinline__ uint32_t split_one(float v) {
+  if constexpr (F16) {
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn((v - __half2float(hi)) * kTailScaleF16);
+    return (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+  } else {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    return pack_bf16(hi, lo);
+  }
+}
 
 template <int RT, bool JIT = false>
 struct Cfg {
@@ -124,9 +166,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M x N
-__device__ __host__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// kind::f16 instruction descriptor: D = f32, A = B = bf16 (format 1) or fp16 (format 0), both K-major, M x N
+__device__ __host__ constexpr uint32_t make_idesc(int M, int N, bool f16 = false) {
+  return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -142,28 +184,30 @@ __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t d
 //                    D[:, 0:RT]  += W_tail * A_head               (N = RT)
 // and the epilogue adds the two halves of D.  Descriptors advance by one add per k16 step (+32 bytes = +2 in the
 // 16-byte address field); the accumulate predicates are set up once.
-__device__ __forceinline__ void mma_chunk_x3(uint32_t tmem_d, uint32_t idesc_2n, uint32_t idesc_n, uint64_t wh,
+// tmem_d2: where the W_tail * A_head product goes -- tmem_d (bf16x3: one sum) or tmem_d + RT columns (fp16x3: the
+// accumulator of the scaled correction terms, see kTailScaleF16).
+__device__ __forceinline__ void mma_chunk_x3(uint32_t tmem_d, uint32_t tmem_d2, uint32_t idesc_2n, uint32_t idesc_n, uint64_t wh,
                                              uint64_t wl, uint64_t a, uint32_t acc_first) {
   asm volatile(
       "{\n\t"
       ".reg .pred p0, p1;\n\t"
       ".reg .b64 wh, wl, a;\n\t"
-      "setp.ne.b32 p0, %6, 0;\n\t"
-      "setp.eq.b32 p1, %6, %6;\n\t"
-      "mov.b64 wh, %3;\n\tmov.b64 wl, %4;\n\tmov.b64 a, %5;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, a, %1, p0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wl, a, %2, p1;\n\t"
+      "setp.ne.b32 p0, %7, 0;\n\t"
+      "setp.eq.b32 p1, %7, %7;\n\t"
+      "mov.b64 wh, %4;\n\tmov.b64 wl, %5;\n\tmov.b64 a, %6;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, a, %2, p0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], wl, a, %3, p1;\n\t"
       "add.s64 wh, wh, 2;\n\tadd.s64 wl, wl, 2;\n\tadd.s64 a, a, 2;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, a, %1, p1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wl, a, %2, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, a, %2, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], wl, a, %3, p1;\n\t"
       "add.s64 wh, wh, 2;\n\tadd.s64 wl, wl, 2;\n\tadd.s64 a, a, 2;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, a, %1, p1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wl, a, %2, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, a, %2, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], wl, a, %3, p1;\n\t"
       "add.s64 wh, wh, 2;\n\tadd.s64 wl, wl, 2;\n\tadd.s64 a, a, 2;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, a, %1, p1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], wl, a, %2, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], wh, a, %2, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%1], wl, a, %3, p1;\n\t"
       "}\n" ::"r"(tmem_d),
-      "r"(idesc_2n), "r"(idesc_n), "l"(wh), "l"(wl), "l"(a), "r"(acc_first)
+      "r"(tmem_d2), "r"(idesc_2n), "r"(idesc_n), "l"(wh), "l"(wl), "l"(a), "r"(acc_first)
       : "memory");
 }
 __device__ __forceinline__ void mma_chunk_x1(uint32_t tmem_d, uint32_t idesc, uint64_t wh, uint64_t ah, uint32_t acc_first) {
@@ -280,7 +324,7 @@ __device__ __forceinline__ void jit_chunk_load(uint32_t stage_a, uint32_t w1off,
 #pragma unroll
   for (int k = 0; k < KB; ++k) lds128_2x64(w1_a + (k * kKC) * 4, w[k][0], w[k][1]);
 }
-template <int KB, int APLANE>
+template <int KB, int APLANE, bool F16>
 __device__ __forceinline__ void jit_chunk_compute(uint32_t stage_a, int j, int lane, const float (&x)[4][KB],
                                                   const uint64_t (&w)[KB + 1][2]) {
   const int q = lane >> 2, fq = lane & 3;
@@ -305,10 +349,7 @@ __device__ __forceinline__ void jit_chunk_compute(uint32_t stage_a, int j, int l
       float a0, a1;
       unpack2(acc[rr][c], a0, a1);
       a0 = leaky(a0), a1 = leaky(a1);
-      const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);  // .x = a0 (low half), one instruction
-      hb[c] = *reinterpret_cast<const uint32_t*>(&h2);
-      const __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - __uint_as_float(hb[c] << 16), a1 - __uint_as_float(hb[c] & 0xffff0000u));
-      lb[c] = *reinterpret_cast<const uint32_t*>(&l2);
+      split_pair<F16>(a0, a1, hb[c], lb[c]);
     }
     const uint32_t off = tile_off_bytes(q + 8 * rr, f0);
     sts64u(stage_a + kWChunkU + off, hb[0], hb[1]);
@@ -321,7 +362,7 @@ __device__ __forceinline__ void jit_chunk_compute(uint32_t stage_a, int j, int l
 // load per k and lane, packed fp32 FMAs in the original order): the head/tail halves go straight to the producer's slot
 // of the global scratch ring with 8-byte stores.  The thread-per-feature version it replaces spent most of its time on
 // broadcast 128-bit loads of the inputs (a quarter warp per bank phase): 7.2 us per subnet at 128 rows.
-template <int KB, int APLANE>
+template <int KB, int APLANE, bool F16>
 __device__ __forceinline__ void first_layer_tile(uint32_t w_a, uint32_t b_a, const float (&x)[4][KB], int rb, int fb, int lane,
                                                  uint8_t* dst_chunk0, int chunk_bytes) {
   const int q = lane >> 2, fq = lane & 3;
@@ -350,10 +391,7 @@ __device__ __forceinline__ void first_layer_tile(uint32_t w_a, uint32_t b_a, con
       float a0, a1;
       unpack2(acc[rr][c], a0, a1);
       a0 = leaky(a0), a1 = leaky(a1);
-      const __nv_bfloat162 h2 = __floats2bfloat162_rn(a0, a1);
-      hb[c] = *reinterpret_cast<const uint32_t*>(&h2);
-      const __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - __uint_as_float(hb[c] << 16), a1 - __uint_as_float(hb[c] & 0xffff0000u));
-      lb[c] = *reinterpret_cast<const uint32_t*>(&l2);
+      split_pair<F16>(a0, a1, hb[c], lb[c]);
     }
     const uint32_t off = tile_off_bytes(rb * 32 + q + 8 * rr, f0 & 63);
     stg64(dst + off, hb[0], hb[1]);
@@ -361,7 +399,7 @@ __device__ __forceinline__ void first_layer_tile(uint32_t w_a, uint32_t b_a, con
   }
 }
 
-template <int RT, bool JIT = false>
+template <int RT, bool JIT = false, bool F16 = false>
 __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_kernel(const FlowParams p) {
   using C = Cfg<RT, JIT>;
   constexpr int kStages = C::kStages;
@@ -451,7 +489,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
       const uint32_t use = ((uint32_t)g * (uint32_t)p.n_big * (uint32_t)KCH + (uint32_t)i) / kStages;
       if (use > 0) mbar_wait(&sm.empty[st], (use - 1) & 1);
       if (tb) tb[32 + (i >> 1)] = clock64();
-      if (!(p.debug & 2048)) jit_chunk_compute<KB, C::kAPlane>(stage_a, j, lane, xx, w);
+      if (!(p.debug & 2048)) jit_chunk_compute<KB, C::kAPlane, F16>(stage_a, j, lane, xx, w);
       if (tb) tb[48 + (i >> 1)] = clock64();
       if (!(p.debug & 1024)) fence_proxy_async_smem();  // generic-proxy writes -> the tensor core's (async proxy) reads
       bar_gen_group(grp);
@@ -607,8 +645,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
                   if (lane == 0) {
                     if (ld_relaxed(p.status + 1) == launch_id) bail = 1;
                     else if (clock64() - t0 > 2500000000LL) {
-                      atomicOr(p.status, IKF_STATUS_SYNC_TIMEOUT);
-                      atomicExch(p.status + 1, launch_id);
+                      report_timeout(p.status, p.status_host, launch_id);
                       bail = 1;
                     }
                   }
@@ -645,14 +682,15 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
     // loop ("once per active thread"); behind elect.sync the UTCHMMAs are emitted back to back: 840 -> 560 cycles per
     // k-chunk for the issuing thread (scripts/ubench/umma_loop.cu), which is what paces the hidden layers. =====
     {
-      constexpr uint32_t idesc = make_idesc(kFTU, RT);       // N = RT
-      constexpr uint32_t idesc2 = make_idesc(kFTU, 2 * RT);  // N = 2 RT: activation head and tail stacked
+      constexpr uint32_t idesc = make_idesc(kFTU, RT, F16);       // N = RT
+      constexpr uint32_t idesc2 = make_idesc(kFTU, 2 * RT, F16);  // N = 2 RT: activation head and tail stacked
       uint32_t ring_pos = 0;
       uint32_t layers = 0;  // hidden layers issued so far
-      const bool x3 = p.precision == IKF_PRECISION_BF16X3;
+      const bool x3 = p.precision != IKF_PRECISION_BF16X1;
       const uint64_t d_wh0 = make_desc(smem_u32(sm.ring[0])), d_wl0 = make_desc(smem_u32(sm.ring[0]) + kWPlaneU);
       const uint64_t d_a0 = make_desc(smem_u32(sm.ring[0]) + kWChunkU);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint32_t tmem_u2 = tmem_u + (F16 ? RT : 0);  // fp16x3: the scaled correction terms have their own accumulator
       const bool static_ring = (KCH % kStages) == 0;  // every layer then starts at ring stage 0
       for (int g = 0; g < total_steps; ++g) {
         for (int l = 0; l < p.n_big; ++l) {
@@ -671,7 +709,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
                 constexpr uint64_t kStageOff = (uint64_t)(C::kStage >> 4);  // stage offset in the 16-byte address field
                 if (elect_one()) {
                   if (x3)
-                    mma_chunk_x3(tmem_u, idesc2, idesc, d_wh0 + s * kStageOff, d_wl0 + s * kStageOff, d_a0 + s * kStageOff, (i0 + s) != 0);
+                    mma_chunk_x3(tmem_u, tmem_u2, idesc2, idesc, d_wh0 + s * kStageOff, d_wl0 + s * kStageOff, d_a0 + s * kStageOff, (i0 + s) != 0);
                   else
                     mma_chunk_x1(tmem_u, idesc, d_wh0 + s * kStageOff, d_a0 + s * kStageOff, (i0 + s) != 0);
                   mma_commit(&sm.empty[s]);  // the stage is free once these MMAs have read it
@@ -689,7 +727,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
               const uint64_t soff = (uint64_t)(s * (C::kStage >> 4));
               if (elect_one()) {
                 if (x3)
-                  mma_chunk_x3(tmem_u, idesc2, idesc, d_wh0 + soff, d_wl0 + soff, d_a0 + soff, i != 0);
+                  mma_chunk_x3(tmem_u, tmem_u2, idesc2, idesc, d_wh0 + soff, d_wl0 + soff, d_a0 + soff, i != 0);
                 else
                   mma_chunk_x1(tmem_u, idesc, d_wh0 + soff, d_a0 + soff, i != 0);
                 mma_commit(&sm.empty[s]);
@@ -718,7 +756,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
     uint32_t act_w[2] = {0, 0};  // publishes so far into each activation scratch buffer
     uint32_t axchg = 0;          // activation exchanges so far
     uint32_t layers = 0;         // hidden layers drained so far
-    const bool x3 = p.precision == IKF_PRECISION_BF16X3;
+    const bool x3 = p.precision != IKF_PRECISION_BF16X1;
     const uint32_t vt_a = smem_u32(sm.vt[h]);
     const int j8 = lane & 7;     // publish: row inside an 8-row block after the lane transpose
     const uint32_t xin_a = smem_u32(&sm.a[0][0]);
@@ -824,7 +862,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
                 }
 #pragma unroll
               for (int ti = 0; ti < kTilesPerWarp; ++ti)
-                first_layer_tile<KB, C::kAPlane>(sp_a + (kSmFirstW - C::kSmShift) * 4, sp_a + (kSmFirstB - C::kSmShift) * 4, x, rb, fb0 + ti,
+                first_layer_tile<KB, C::kAPlane, F16>(sp_a + (kSmFirstW - C::kSmShift) * 4, sp_a + (kSmFirstB - C::kSmShift) * 4, x, rb, fb0 + ti,
                                                  lane, dst0, C::kAChunk);
             };
             if (kin <= 12) run(std::integral_constant<int, 12>{});
@@ -867,11 +905,11 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
 #pragma unroll
               for (int c0 = 0; c0 < ER; c0 += 32) {
                 float tmp[32], tmp2[32];
-                tmem_ld32(taddr + row0 + c0, tmp);  // W_head*A_head + W_tail*A_head
+                tmem_ld32(taddr + row0 + c0, tmp);  // bf16x3: W_head*A_head + W_tail*A_head; fp16x3: W_head*A_head
                 if (x3) {
-                  tmem_ld32(taddr + RT + row0 + c0, tmp2);  // W_head*A_tail
+                  tmem_ld32(taddr + RT + row0 + c0, tmp2);  // bf16x3: W_head*A_tail; fp16x3: 2^11 (W_head*A_tail + W_tail*A_head)
 #pragma unroll
-                  for (int r = 0; r < 32; ++r) v[c0 + r] = tmp[r] + tmp2[r];
+                  for (int r = 0; r < 32; ++r) v[c0 + r] = F16 ? fmaf(tmp2[r], 1.f / kTailScaleF16, tmp[r]) : tmp[r] + tmp2[r];
                 } else {
 #pragma unroll
                   for (int r = 0; r < 32; ++r) v[c0 + r] = tmp[r];
@@ -899,11 +937,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
               for (int r0 = 0; r0 < ER; r0 += 8) {
                 uint32_t wd[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const __nv_bfloat16 hi = __float2bfloat16_rn(v[r0 + i]);
-                  const __nv_bfloat16 lo = __float2bfloat16_rn(v[r0 + i] - __bfloat162float(hi));
-                  wd[i] = pack_bf16(hi, lo);  // head in the low half, tail in the high half
-                }
+                for (int i = 0; i < 8; ++i) wd[i] = split_one<F16>(v[r0 + i]);  // head in the low half, tail in the high half
                 // before: lane j8 (feature kf8 + j8) holds rows r0..r0+7; after: lane j8 holds row r0 + j8, features kf8..kf8+7
 #pragma unroll
                 for (int st = 4; st >= 1; st >>= 1) {
@@ -1061,8 +1095,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
                   if ((spins & 255u) == 0) {
                     if (ld_relaxed(p.status + 1) == launch_id) break;
                     if (clock64() - t0 > 2500000000LL) {
-                      atomicOr(p.status, IKF_STATUS_SYNC_TIMEOUT);
-                      atomicExch(p.status + 1, launch_id);
+                      report_timeout(p.status, p.status_host, launch_id);
                       break;
                     }
                   }
@@ -1111,11 +1144,13 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
           if (p.finalize) {
             o = 0.f;
             for (int k = 0; k < p.W; ++k) o = fmaf(sm.u[r][k] - p.flt_b[k], p.m_inv[k * kPad + j], o);
-            if (p.clamp_out && j < p.ndof) o = fminf(fmaxf(o, p.lo[j]), p.hi[j]);
+            // NaN / inf are reported BEFORE the clamp, and NaN survives it as in torch.clamp (robot.clamp_to_joint_limits)
+            if (!isfinite(o)) report_nonfinite(p.status, p.status_host);
+            if (p.clamp_out && j < p.ndof && o == o) o = fminf(fmaxf(o, p.lo[j]), p.hi[j]);
           } else {
             o = sm.u[r][j];
+            if (!isfinite(o)) report_nonfinite(p.status, p.status_host);
           }
-          if (!isfinite(o)) atomicOr(p.status, IKF_STATUS_NONFINITE);
           p.out[(size_t)row * p.out_ld + j] = o;
         }
         if (p.forward && p.logdet_out != nullptr)

@@ -51,6 +51,7 @@ struct RobotDev {
 struct IkfRobot {
   ikf::RobotDev dev;
   int device;
+  double lo64[ikf::kMaxDof], hi64[ikf::kMaxDof];  // the limits as given (the sampler maps its uniforms in fp64)
 };
 
 namespace ikf {
@@ -195,7 +196,8 @@ __device__ __forceinline__ void pose_error(const float* cur, const float* tgt, f
   *rot_err = fabsf(r - pi);
 }
 
-__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+// torch.clamp semantics: NaN stays NaN (fminf / fmaxf alone would turn it into a limit)
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return x != x ? x : fminf(fmaxf(x, lo), hi); }
 
 // One LM step for the sample owned by this group.  Returns the new value of joint j (lanes >= ndof return 0).
 // e = [rpy(q_t (x) q_cur^-1); p_t - p_cur], J rows 0-2 angular / 3-5 linear, dq = solve(J^T J + lambd I, J^T e).
@@ -434,6 +436,61 @@ __global__ void __launch_bounds__(kThreads) lm_refine_kernel(RobotDev rb, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Target-pose generator: q ~ U(lo + eps, hi - eps) per joint, poses = FK(q), one launch (the step before the hot path:
+// jrl Robot.sample_joint_angles_and_poses, called at scripts/benchmark_runtime.py:83-86, scripts/evaluate.py:137-139,
+// tests/ikflow_solver_test.py:70-72; the klampt self-collision rejection stays out).
+//
+// Counter-based RNG, Philox4x32-10 (Salmon et al., SC'11): key = 64-bit seed, counter = (sample index lo, hi, block, 0).
+// Sample s, joint j uses word j % 4 of block j / 4; u = (word + 0.5) * 2^-32 in (0, 1), mapped in fp64 and rounded to
+// fp32 once -- the arithmetic of the oracle's sampler.  A sample depends only on (seed, s): any partition of the index
+// range over launches, streams or GPUs gives the same samples.
+
+struct SampleLimits {
+  double lo[kMaxDof], span[kMaxDof];
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}
+
+__global__ void __launch_bounds__(kThreads) sample_kernel(RobotDev rb, SampleLimits lim, uint64_t seed, uint64_t first,
+                                                          float* __restrict__ q_out, float* __restrict__ poses, int m) {
+  const int j = threadIdx.x % kGroup;
+  const int s = (blockIdx.x * kThreads + threadIdx.x) / kGroup;
+  const bool live = s < m;
+  const uint64_t idx = first + (uint64_t)(live ? s : 0);
+  uint32_t w[4];
+  philox4x32_10((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)(j >> 2), 0u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+  const uint32_t word = (j & 3) == 0 ? w[0] : (j & 3) == 1 ? w[1] : (j & 3) == 2 ? w[2] : w[3];
+  const double u = ((double)word + 0.5) * (1.0 / 4294967296.0);
+  // no FMA contraction: the oracle evaluates lo + u * (hi - lo) with two roundings in fp64
+  const float qj = (live && j < rb.ndof) ? (float)__dadd_rn(lim.lo[j], __dmul_rn(u, lim.span[j])) : 0.f;
+  if (live && j < rb.ndof) q_out[(size_t)s * rb.ndof + j] = qj;
+  const Chain ch = chain_scan(rb, j, qj);
+  float pose[7];
+  ee_pose(ch.ee, pose);
+  if (live && j < 7) {
+    float v = pose[0];
+#pragma unroll
+    for (int i = 1; i < 7; ++i)
+      if (j == i) v = pose[i];
+    poses[(size_t)s * 7 + j] = v;
+  }
+}
+
 static inline int grid_for(int samples) { return (samples * kGroup + kThreads - 1) / kThreads; }
 
 static void mat_mul_3x4(const double* a, const double* b, double* c) {
@@ -490,6 +547,8 @@ int ikf_robot_create(int n_links, const int32_t* kind, const double* fixed_T, co
     for (int i = 0; i < 3; ++i) r->dev.axis[nd][i] = (float)(a[i] / nrm);
     r->dev.lo[nd] = (float)lo[nd];
     r->dev.hi[nd] = (float)hi[nd];
+    r->lo64[nd] = lo[nd];
+    r->hi64[nd] = hi[nd];
     std::memcpy(acc, ident, sizeof(acc));
     ++nd;
   }
@@ -531,6 +590,24 @@ int ikf_forward_kinematics(IkfRobot* robot, const float* q, float* poses_out, in
   if (!q || !poses_out) return fail(IKF_EINVAL, "ikf_forward_kinematics: NULL tensor");
   fk_kernel<<<grid_for(m), kThreads, 0, st>>>(robot->dev, q, poses_out, m);
   IKF_LAUNCH_CHECK("ikf_forward_kinematics");
+  return IKF_OK;
+}
+
+int ikf_sample_joint_angles_and_poses(IkfRobot* robot, uint64_t seed, uint64_t first_index, double joint_limit_eps,
+                                      float* q_out, float* poses_out, int m, void* stream) {
+  IKF_ROBOT_PROLOGUE("ikf_sample_joint_angles_and_poses");
+  if (!q_out || !poses_out) return fail(IKF_EINVAL, "ikf_sample_joint_angles_and_poses: NULL tensor");
+  if (!(joint_limit_eps >= 0.0)) return fail(IKF_EINVAL, "ikf_sample_joint_angles_and_poses: negative joint_limit_eps");
+  SampleLimits lim;
+  for (int j = 0; j < kMaxDof; ++j) {
+    const double lo = j < robot->dev.ndof ? robot->lo64[j] + joint_limit_eps : 0.0;
+    const double hi = j < robot->dev.ndof ? robot->hi64[j] - joint_limit_eps : 0.0;
+    if (hi < lo) return fail(IKF_EINVAL, "ikf_sample_joint_angles_and_poses: joint %d has an empty range", j);
+    lim.lo[j] = lo;
+    lim.span[j] = hi - lo;
+  }
+  sample_kernel<<<grid_for(m), kThreads, 0, st>>>(robot->dev, lim, seed, first_index, q_out, poses_out, m);
+  IKF_LAUNCH_CHECK("ikf_sample_joint_angles_and_poses");
   return IKF_OK;
 }
 

@@ -25,6 +25,8 @@ def all_gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tens
     world = dist.get_world_size(group)
     if world == 1:
         return local
+    if n_total == 0:
+        return local
     sizes = [shard_bounds(n_total, r, world)[1] - shard_bounds(n_total, r, world)[0] for r in range(world)]
     if len(set(sizes)) == 1:
         out = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
@@ -44,20 +46,32 @@ def generate_ik_solutions_sharded(
 ) -> torch.Tensor:
     """``solver.generate_ik_solutions`` for the rows of this rank (``target_poses`` / ``latent`` hold ALL n rows on
     every rank, as after a broadcast), followed by the single all-gather of the joint angles."""
+    assert target_poses.dim() == 2 and target_poses.shape[1] == 7, f"target_poses must be [n x 7], got {tuple(target_poses.shape)}"
     n = target_poses.shape[0]
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     lo, hi = shard_bounds(n, rank, world)
-    local_latent = None if latent is None else latent[lo:hi]
-    local = solver.generate_ik_solutions(target_poses[lo:hi], None, latent=local_latent, **kwargs)
+    if hi == lo:
+        # n < world_size: this rank has no row.  It must still take part in the collective (a rank that raised here
+        # would leave the others blocked in the all-gather).
+        local = torch.empty((0, solver.ndof), dtype=torch.float32, device=target_poses.device)
+    else:
+        local_latent = None if latent is None else latent[lo:hi]
+        # n=hi-lo: a one-row shard is a [1 x 7] tensor, which generate_ik_solutions reads as "a single pose, n solutions"
+        local = solver.generate_ik_solutions(target_poses[lo:hi], hi - lo, latent=local_latent, **kwargs)
     return all_gather_rows(local, n, group) if gather else local
 
 
 def generate_exact_ik_solutions_sharded(solver, target_poses: torch.Tensor, gather: bool = True, group=None, **kwargs):
     """Pose-sharded ``generate_exact_ik_solutions`` (all repeats of a pose stay on one GPU)."""
+    assert target_poses.dim() == 2 and target_poses.shape[1] == 7, f"target_poses must be [n x 7], got {tuple(target_poses.shape)}"
     n = target_poses.shape[0]
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     lo, hi = shard_bounds(n, rank, world)
-    sol, valid = solver.generate_exact_ik_solutions(target_poses[lo:hi], **kwargs)
+    if hi == lo:  # no pose for this rank (n < world_size): empty shard, but stay in the collective
+        sol = torch.empty((0, solver.ndof), dtype=torch.float32, device=target_poses.device)
+        valid = torch.empty((0,), dtype=torch.bool, device=target_poses.device)
+    else:
+        sol, valid = solver.generate_exact_ik_solutions(target_poses[lo:hi], **kwargs)
     if not gather:
         return sol, valid
     packed = torch.cat([sol, valid.to(sol.dtype).unsqueeze(1)], dim=1)  # one collective for both

@@ -69,5 +69,6 @@ def evaluate_solutions(robot, target_poses: torch.Tensor, solutions: torch.Tenso
     if not _warned_self_collision:
         warnings.warn("ikflow_b200 does not check self-collisions: the self_collisions entry is all False")
         _warned_self_collision = True
-    self_collisions = torch.zeros(solutions.shape[0], dtype=torch.bool)
+    # (the reference builds this one tensor on the CPU, evaluation_utils.py:124-127; here all four live with the solutions)
+    self_collisions = torch.zeros(solutions.shape[0], dtype=torch.bool, device=solutions.device)
     return l2_errors, angular_errors, joint_limits_exceeded, self_collisions

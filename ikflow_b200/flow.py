@@ -27,7 +27,7 @@ class FlowModel:
         assert params.coupling_layer == "glow", "only the GLOW coupling block is implemented (all released models)"
         assert not getattr(params, "sigmoid_on_output", False), "sigmoid_on_output is not used by any released model"
         assert params.permute_random_enabled, "permute_random_enabled=False is not supported"
-        assert precision in ("bf16x3", "bf16x1")
+        assert precision in ("bf16x3", "bf16x1", "fp16x3")
         self.params = params
         self.ndim_tot = int(ndim_tot)
         self.dim_cond = int(dim_cond)
@@ -96,7 +96,7 @@ class FlowModel:
     def _desc(self) -> _lib.IkfFlowDesc:
         return _lib.IkfFlowDesc(
             self.ndim_tot, self.dim_cond, self.nb_nodes, self.coeff_fn_config, self.hidden, self.ndof, self.rnvp_clamp,
-            _lib.IKF_PRECISION_BF16X3 if self.precision == "bf16x3" else _lib.IKF_PRECISION_BF16X1,
+            {"bf16x3": _lib.IKF_PRECISION_BF16X3, "bf16x1": _lib.IKF_PRECISION_BF16X1, "fp16x3": _lib.IKF_PRECISION_FP16X3}[self.precision],
         )
 
     def flat_weights(self) -> np.ndarray:
@@ -210,6 +210,19 @@ class FlowModel:
         code = _lib.lib().ikf_flow_status(self._handle(dev), torch.cuda.current_stream(dev).cuda_stream, ctypes.byref(word))
         _lib.check(code, "ikf_flow_status")
         return int(word.value)
+
+    def poll_status(self, device=None) -> int:
+        """The status bits WITHOUT synchronising (``ikf_flow_poll_status``: a mirror the kernels keep in mapped host
+        memory).  A launch that timed out (``IKF_STATUS_SYNC_TIMEOUT``) additionally makes the NEXT call on the handle
+        raise ``IkflowB200Error`` (code ``IKF_ESTATUS``)."""
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        word = ctypes.c_uint32(0)
+        _lib.check(_lib.lib().ikf_flow_poll_status(self._handle(dev), ctypes.byref(word)), "ikf_flow_poll_status")
+        return int(word.value)
+
+    def last_kernel(self, device=None) -> str:
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        return _lib.lib().ikf_flow_last_kernel(self._handle(dev)).decode()
 
     def info(self, device=None) -> Dict[str, int]:
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())

@@ -141,7 +141,10 @@ def make_synthetic_state_dict(
     return sd
 
 
-def glow_cNF_model(params: IkflowModelParameters, robot, dim_cond: int, ndim_tot: int, precision: str = "bf16x3"):
+DEFAULT_PRECISION = "bf16x3"
+
+
+def glow_cNF_model(params: IkflowModelParameters, robot, dim_cond: int, ndim_tot: int, precision: Optional[str] = None):
     """Build the conditional flow for ``robot`` -- ``ikflow/model.py:291-356``.
 
     The reference wires FrEIA nodes (FixedLinearTransform, then ``nb_nodes`` x [PermuteRandom(seed=i),
@@ -149,8 +152,17 @@ def glow_cNF_model(params: IkflowModelParameters, robot, dim_cond: int, ndim_tot
     :class:`ikflow_b200.flow.FlowModel`, whose reverse pass is a single sm_100a kernel.  The weights (including the
     FixedLinearTransform matrices and the permutation tables) arrive through ``load_state_dict`` exactly as in the
     reference.
+
+    ``precision``: operand format of the hidden-layer tensor-core products, ``"bf16x3"`` / ``"fp16x3"`` (parity grade, see
+    ``include/ikflow_b200.h``) or ``"bf16x1"`` (fast, NOT parity grade); default ``IKFLOW_B200_PRECISION`` or
+    ``DEFAULT_PRECISION``.
     """
+    import os
+
     from .flow import FlowModel
+
+    if precision is None:
+        precision = os.environ.get("IKFLOW_B200_PRECISION", DEFAULT_PRECISION)
 
     assert ndim_tot >= robot.ndof, f"network width {ndim_tot} is smaller than the robot's {robot.ndof} dofs"
     return FlowModel(params, robot.actuated_joints_limits, dim_cond, ndim_tot, precision=precision)

@@ -225,26 +225,40 @@ class Robot:
         return final_q, valid.bool(), n_valid
 
     # ---- sampling (the step before the hot path) --------------------------------------------------------------------
-    def sample_joint_angles(self, n: int, joint_limit_eps: float = 1e-6, generator=None, device=None) -> torch.Tensor:
-        device = device or _default_device()
-        lims = torch.tensor(self.actuated_joints_limits, dtype=torch.float64)
-        lo, hi = lims[:, 0] + joint_limit_eps, lims[:, 1] - joint_limit_eps
-        u = torch.rand((n, self.ndof), generator=generator, dtype=torch.float64)
-        return (lo + u * (hi - lo)).to(torch.float32).to(device)
-
     def sample_joint_angles_and_poses(
         self, n: int, joint_limit_eps: float = 1e-6, only_non_self_colliding: bool = False, tqdm_enabled: bool = False,
-        return_torch: bool = False, generator=None, device=None,
+        return_torch: bool = False, seed: Optional[int] = None, first_index: int = 0, generator=None, device=None,
     ):
-        """Uniform joint samples inside the limits and their FK poses.  jrl returns numpy arrays (``return_torch=False``).
+        """Uniform joint samples inside the limits and their FK poses -- jrl ``Robot.sample_joint_angles_and_poses``
+        (``scripts/benchmark_runtime.py:83-86``, ``scripts/evaluate.py:137-139``) in ONE kernel launch: a counter-based
+        Philox4x32-10 draw per (sample, joint) and the forward kinematics of the sample (``ikf_sample_joint_angles_and_poses``).
+        Nothing is drawn on the host and nothing crosses PCIe unless numpy arrays are asked for (jrl's return type,
+        ``return_torch=False``).
+
+        ``seed``: 64-bit key of the stream; ``None`` draws one from ``generator`` (default: torch's global CPU generator,
+        so ``torch.manual_seed`` / the reference's ``set_seed`` make the samples reproducible).  Sample ``i`` depends
+        only on ``(seed, first_index + i)``: shards of one index range are the same whatever the split.
         The self-collision rejection of jrl needs klampt capsule geometry, which is outside this package."""
         if only_non_self_colliding:
             warnings.warn("ikflow_b200 has no self-collision checker: samples are NOT filtered for self-collisions")
-        q = self.sample_joint_angles(n, joint_limit_eps, generator, device)
-        poses = self.forward_kinematics(q)
+        assert isinstance(n, int) and n >= 0
+        device = torch.device(device or _default_device())
+        if seed is None:
+            seed = int(torch.randint(0, 2**62, (1,), generator=generator).item())
+        q = torch.empty((n, self.ndof), dtype=torch.float32, device=device)
+        poses = torch.empty((n, 7), dtype=torch.float32, device=device)
+        code = _lib.lib().ikf_sample_joint_angles_and_poses(
+            self._handle(device), int(seed) & (2**64 - 1), int(first_index), float(joint_limit_eps), q.data_ptr(),
+            poses.data_ptr(), n, _stream_ptr(q),
+        )
+        _lib.check(code, "ikf_sample_joint_angles_and_poses")
         if return_torch:
             return q, poses
         return q.cpu().numpy(), poses.cpu().numpy()
+
+    def sample_joint_angles(self, n: int, joint_limit_eps: float = 1e-6, seed: Optional[int] = None, generator=None, device=None) -> torch.Tensor:
+        """jrl ``Robot.sample_joint_angles``: the joint half of :meth:`sample_joint_angles_and_poses` (torch tensor)."""
+        return self.sample_joint_angles_and_poses(n, joint_limit_eps, return_torch=True, seed=seed, generator=generator, device=device)[0]
 
 
 def _default_device() -> str:
@@ -320,6 +334,14 @@ _ROBOTS = {"panda": Panda, "fetch": Fetch, "fetch_arm": FetchArm}
 
 def get_robot(robot_name: str) -> Robot:
     """jrl ``get_robot(name)`` (``ikflow/model_loading.py:81-83``)."""
+    if robot_name == "rizon4":
+        raise ValueError(
+            "robot 'rizon4' (model 'rizon4__snowy-brook-208__global_step=2.75M', ikflow/model_descriptions.yaml:90-97) is "
+            "registered but its kinematic chain is not available in ikflow_b200: the reference tree ships no URDF or test "
+            "constant for the Flexiv Rizon 4 (they live in the un-vendored jrl package), so its joint limits and link "
+            "transforms cannot be reproduced offline.  Pass your own chain: ikflow_b200.Robot('rizon4', [Joint(...), ...]) "
+            "as the `robot` argument of get_ik_solver()."
+        )
     if robot_name not in _ROBOTS:
         raise ValueError(f"Unable to find robot '{robot_name}' (available: {sorted(_ROBOTS)})")
     return _ROBOTS[robot_name]()

@@ -18,7 +18,10 @@
  *     no hidden host synchronisation (exceptions are documented);
  *   - return 0 on success, a negative IKF_E* code otherwise; never throws.  ikf_last_error() returns a thread-local
  *     human-readable message for the last failing call;
- *   - a handle may be used by one stream at a time (it owns the activation workspace).
+ *   - handles are re-entrant: any number of host threads and streams may share one.  A flow handle owns one exchange
+ *     workspace and a launch occupies every SM, so the library serialises its launches (a mutex on the host side, an
+ *     event wait when consecutive launches come from different streams); results are those of the calls in submission
+ *     order.  Inside a CUDA stream capture use one capturing stream per handle.
  */
 #ifndef IKFLOW_B200_H_
 #define IKFLOW_B200_H_
@@ -35,10 +38,14 @@ extern "C" {
 #define IKF_ECUDA (-2)    /* CUDA runtime error (see ikf_last_error) */
 #define IKF_ENOMEM (-3)   /* device allocation failed */
 #define IKF_EDEVICE (-4)  /* device is not an sm_100 part / kernel image not loadable */
+#define IKF_ESTATUS (-5)  /* an EARLIER launch on the handle reported IKF_STATUS_SYNC_TIMEOUT (its output is invalid) */
 
-/* status bits reported by ikf_flow_status */
-#define IKF_STATUS_NONFINITE 1u    /* a hidden activation or an output was not finite */
-#define IKF_STATUS_SYNC_TIMEOUT 2u /* an inter-CTA dependency wait timed out (results invalid) */
+/* status bits reported by ikf_flow_status / ikf_flow_poll_status */
+#define IKF_STATUS_NONFINITE 1u    /* an output was not finite (NaN / inf inputs propagate, as in the reference) */
+#define IKF_STATUS_SYNC_TIMEOUT 2u /* an inter-CTA dependency wait timed out after ~1.3 s (results invalid): the teams of a
+                                      launch spin on each other's flags, so a co-tenant kernel that holds SMs can stall
+                                      it; the kernel then gives up instead of hanging the GPU, writes this bit into
+                                      mapped host memory, and the NEXT call on the handle fails with IKF_ESTATUS */
 
 #define IKF_MAX_WIDTH 16  /* dim_latent_space */
 #define IKF_MAX_LINKS 16  /* links on the kinematic chain (fixed + actuated) */
@@ -66,6 +73,12 @@ typedef struct {
  * BF16X1 is the single-product fast mode (about 1e-2 abs): NOT parity grade, reported separately. */
 #define IKF_PRECISION_BF16X3 0
 #define IKF_PRECISION_BF16X1 1
+/* FP16X3: fp16 head + fp16 tail scaled by 2^11 (22 mantissa bits), the two correction products in their own fp32
+ * accumulator: as close to the fp32 reference as fp32 is to fp64 (5e-6 abs on the synthetic Panda weights, 1e-5 with the
+ * last layers x2 where BF16X3 is at 2e-4) for the same three products.  Range of fp16: hidden activations must stay
+ * below 65504 in magnitude (they are O(1) for a trained network); beyond it outputs are NaN and IKF_STATUS_NONFINITE
+ * is raised.  tcgen05 engine only. */
+#define IKF_PRECISION_FP16X3 2
 
 /* ---- flow --------------------------------------------------------------------------------------------------------
  * ikf_flow_create: replaces glow_cNF_model(...) + nn_model.load_state_dict(...) (ikflow/model.py:291-356,
@@ -84,9 +97,6 @@ void ikf_flow_destroy(IkfFlow* flow);
 
 /* Number of fp32 values ikf_flow_create expects in `weights` for `desc` (0 on invalid desc). */
 size_t ikf_flow_weight_count(const IkfFlowDesc* desc);
-
-/* Pre-size the activation workspace for batches up to max_batch rows (otherwise grown on demand, which synchronises). */
-int ikf_flow_reserve(IkfFlow* flow, int max_batch);
 
 /* ikf_flow_inverse: replaces ikflow_solver.py:98-102 -- the whole reverse pass glow_{nb-1}^-1, perm_{nb-1}^-1, ...,
  * glow_0^-1, perm_0^-1, FixedLinearTransform^-1, followed (optionally) by the joint-limit clamp.
@@ -130,6 +140,13 @@ int ikf_flow_set_forward_tables(IkfFlow* flow, const float* m, float log_det_m);
 /* Reads (and clears) the device status word.  SYNCHRONISES `stream`. */
 int ikf_flow_status(IkfFlow* flow, void* stream, uint32_t* status_out);
 
+/* The same bits WITHOUT synchronising: reads the mirror the kernels keep in mapped host memory (complete for every
+ * launch whose stream has been synchronised; may already show a launch still in flight).  Does not clear. */
+int ikf_flow_poll_status(IkfFlow* flow, uint32_t* status_out);
+
+/* Name of the kernel the last launch on this handle used (for benchmark / profile bookkeeping). */
+const char* ikf_flow_last_kernel(IkfFlow* flow);
+
 /* Introspection for benchmarks: bytes of packed weights resident in HBM, CTAs per launch, dynamic smem per CTA. */
 int ikf_flow_info(IkfFlow* flow, size_t* packed_weight_bytes, int* grid_ctas_last, int* smem_bytes);
 
@@ -152,7 +169,16 @@ int ikf_robot_ndof(const IkfRobot* robot);
 /* robot.forward_kinematics(q[m,ndof]) -> poses[m,7] = [x y z qw qx qy qz]  (ikflow_solver.py:114) */
 int ikf_forward_kinematics(IkfRobot* robot, const float* q, float* poses_out, int m, void* stream);
 
-/* robot.clamp_to_joint_limits(q) in place (ikflow_solver.py:102) */
+/* robot.sample_joint_angles_and_poses(n) minus the self-collision filter (jrl; called at scripts/benchmark_runtime.py:83-86,
+ * scripts/evaluate.py:137-139, tests/ikflow_solver_test.py:70-72): q[s][j] ~ U(lo_j + eps, hi_j - eps), poses = FK(q), one
+ * launch.  Counter-based Philox4x32-10: key = seed, counter = (first_index + s, block j / 4), word j % 4,
+ * u = (word + 0.5) * 2^-32, q = fp32(lo' + u * (hi' - lo')) evaluated in fp64.  Sample s depends only on
+ * (seed, first_index + s), so shards of one index range are independent of how it is split over calls or GPUs.
+ *   q_out [m][ndof], poses_out [m][7] */
+int ikf_sample_joint_angles_and_poses(IkfRobot* robot, uint64_t seed, uint64_t first_index, double joint_limit_eps,
+                                      float* q_out, float* poses_out, int m, void* stream);
+
+/* robot.clamp_to_joint_limits(q) in place (ikflow_solver.py:102); NaN stays NaN (torch.clamp) */
 int ikf_clamp_to_joint_limits(IkfRobot* robot, float* q, int m, void* stream);
 
 /* robot.inverse_kinematics_step_levenburg_marquardt(target_poses, q) (ikflow_solver.py:205,208):

@@ -313,3 +313,13 @@ def sample_joint_angles_and_poses(robot: ChainRobot, n: int, seed: int, dtype=to
     u = torch.rand(n, robot.ndof, generator=g, dtype=torch.float64)
     q = (lims[:, 0] + u * (lims[:, 1] - lims[:, 0])).to(dtype)
     return q, forward_kinematics(robot, q)
+
+
+def joint_angles_from_uniforms(robot: ChainRobot, u: torch.Tensor, joint_limit_eps: float = 1e-6) -> torch.Tensor:
+    """The affine map of jrl's sampler applied to given uniforms ``u`` [n, ndof] in (0, 1), fp64:
+    ``q = lo' + u * (hi' - lo')`` with ``lo' = lo + eps``, ``hi' = hi - eps``, rounded to fp32 once.  The product's
+    device-side sampler (``ikf_sample_joint_angles_and_poses``) is checked against this with the uniforms of
+    ``oracle/philox.py``."""
+    lims = torch.tensor(robot.actuated_joints_limits, dtype=torch.float64)
+    lo, hi = lims[:, 0] + joint_limit_eps, lims[:, 1] - joint_limit_eps
+    return (lo + u.double() * (hi - lo)).to(torch.float32)

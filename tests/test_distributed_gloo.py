@@ -23,12 +23,25 @@ def test_shard_bounds_cover_every_row_once():
 
 
 class _FakeSolver:
+    """Computes a row-wise function, behind the REAL argument checks of the solver (ikflow_solver.py:311-326, 359-362):
+    a [1 x 7] shard is "a single pose" there and needs n, an empty shard must never reach it."""
+
     ndof = 7
 
     def generate_ik_solutions(self, y, n=None, latent=None, **kw):
-        return y * 2.0 + (0.0 if latent is None else latent[:, :7])
+        assert isinstance(y, torch.Tensor)
+        if y.numel() == 7:
+            assert isinstance(n, int)
+            assert n > 0
+        else:
+            assert y.shape[1] == 7
+        n = y.shape[0] if n is None else n
+        assert latent is None or latent.shape[0] == n
+        assert n % y.reshape(-1, 7).shape[0] == 0
+        return y.reshape(-1, 7).expand(n, 7) * 2.0 + (0.0 if latent is None else latent[:, :7])
 
     def generate_exact_ik_solutions(self, y, **kw):
+        assert y.shape[1] == 7 and y.shape[0] > 0
         return y + 1.0, y[:, 0] > 0
 
 
@@ -55,7 +68,7 @@ def _worker(rank, world, port, n, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [512, 7])  # even split and ragged split
+@pytest.mark.parametrize("n", [512, 7, 3, 1, 0])  # even and ragged splits, a one-row shard (n = world + 1), empty shards (n < world)
 def test_sharded_solve_equals_unsharded_world_size_2(n):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

@@ -333,3 +333,158 @@ def test_forward_pass_needs_the_tcgen05_engine(monkeypatch):
     _, poses, cond = _inputs(8, 7)
     with pytest.raises(RuntimeError, match="tcgen05 engine only"):
         model(torch.zeros(8, 7, device=DEV), c=cond.to(DEV), rev=False)
+
+
+# ---- round 2: BASELINE config 4 sizes, precision modes, handle re-entrancy, NaN / status semantics -------------------
+@pytest.mark.parametrize("batch", [1024, 2048, 4096])
+def test_fetch_arm_nb16_large_batches_config4(batch):
+    """fetch_arm__large geometry (width 10, first-layer K = 13 > kJitMaxK, 16 blocks) at the row-group sizes BASELINE
+    config 4 runs at on 1-4 GPUs: 64-row groups (B = 1024) and 128-row groups (B >= 2048) take the tile-by-tile
+    exchanged first layer with the 16-wide input (``first_layer_tile<kPad>``)."""
+    solver, hp, sd = _solver(16, 10, 3, 1024, "fetch_arm")
+    latent = torch.randn(batch, 10, generator=torch.Generator().manual_seed(batch))
+    _, poses = jk.sample_joint_angles_and_poses(jk.FETCH_ARM, batch, seed=batch + 1)
+    cond = torch.cat([poses, torch.zeros(batch, 1)], dim=1)
+    sol = solver.generate_ik_solutions(poses.to(DEV), latent=latent.to(DEV))
+    kernel = solver.nn_model.last_kernel()
+    assert ("<64," in kernel) if batch == 1024 else ("<128," in kernel), kernel
+    idx = torch.arange(0, batch, 8)  # every 8th row keeps the CPU oracle at seconds; rows are independent
+    ref = jk.clamp_to_joint_limits(jk.FETCH_ARM, _oracle(sd, hp, latent[idx], cond[idx])[:, :7].clone())
+    assert (sol.cpu()[idx] - ref).abs().max() < TOL
+    raw = solver.nn_model.inverse(latent.to(DEV), cond.to(DEV))
+    assert (raw.cpu()[idx] - _oracle(sd, hp, latent[idx], cond[idx])).abs().max() < TOL
+    assert torch.equal(sol, solver.generate_ik_solutions(poses.to(DEV), latent=latent.to(DEV)))
+    assert solver.nn_model.status() == 0
+
+
+def _model_with_precision(precision, stress=1.0, nb=12):
+    hp = IkflowModelParameters()
+    hp.nb_nodes, hp.dim_latent_space = nb, 7
+    robot = ikflow_b200.Panda()
+    sd = make_synthetic_state_dict(hp, robot.actuated_joints_limits, seed=0, stress=stress)
+    model = ikflow_b200.glow_cNF_model(hp, robot, 8, 7, precision=precision)
+    model.load_state_dict(sd)
+    return model, hp, sd
+
+
+@pytest.mark.parametrize("batch", [37, 512, 1024, 2048])
+def test_fp16x3_mode_is_as_close_to_fp32_as_fp32_is_to_fp64(batch):
+    """IKF_PRECISION_FP16X3 (fp16 head + 2^11-scaled fp16 tail, separate accumulator for the correction products): every
+    row-group size / kernel instantiation, gate 2e-5 abs against the fp32 oracle (bf16x3: 1e-4) and against fp64."""
+    model, hp, sd = _model_with_precision("fp16x3")
+    latent, poses, cond = _inputs(batch, 7)
+    idx = torch.arange(0, batch, max(1, batch // 256))
+    ref = _oracle(sd, hp, latent[idx], cond[idx])
+    ref64 = freia_flow.flow_inverse(freia_flow.state_dict_to(sd, torch.float64), latent[idx].double(), cond[idx].double(), 12, 3, 2.5)[0]
+    out = model.inverse(latent.to(DEV), cond.to(DEV)).cpu()[idx]
+    assert (out - ref).abs().max() < 2e-5, (out - ref).abs().max()
+    assert (out.double() - ref64).abs().max() < 2e-5
+    assert "true>" in model.last_kernel() and model.status() == 0
+
+
+def test_amplified_weights_x2_need_fp16x3_for_1e4_abs():
+    """Last layer of every subnet x2 (|q| up to ~28: the untrained flow expands): the error of the split-bf16 products
+    grows to ~2e-4 abs -- over the 1e-4 gate -- while fp32 itself is 1.5e-5 from fp64 (scripts/precision_study.py).
+    The fp16x3 mode holds 1e-4 there with margin; bf16x3 is held to 1e-5 RELATIVE and its absolute error is stated."""
+    latent, poses, cond = _inputs(256, 7)
+    errs = {}
+    for precision in ("fp16x3", "bf16x3"):
+        model, hp, sd = _model_with_precision(precision, stress=2.0)
+        ref = _oracle(sd, hp, latent, cond)
+        out = model.inverse(latent.to(DEV), cond.to(DEV)).cpu()
+        errs[precision] = ((out - ref).abs().max().item(), ((out - ref).abs() / (1 + ref.abs())).max().item())
+        assert model.status() == 0
+    assert errs["fp16x3"][0] < 1e-4, errs
+    assert errs["bf16x3"][1] < 2e-5 and errs["bf16x3"][0] < 1e-3, errs
+    print("amplified x2: max abs error fp16x3 %.2e, bf16x3 %.2e" % (errs["fp16x3"][0], errs["bf16x3"][0]))
+
+
+@pytest.mark.parametrize("stress", [3.0, 8.0])
+def test_stress_weights_x3_x8_error_is_that_of_fp32_itself(stress):
+    """SURVEY 8d's stress set (last layers x8) and the x3 set of round 1.  With untrained weights the flow then expands
+    without bound (|q| ~ 5e2 at x3, ~5e8 at x8) and the reference's own fp32 arithmetic is 3e-3 / 1e3 ABSOLUTE from the
+    fp64 value of the same network -- an absolute 1e-4 gate has no meaning there.  Honest statement: relative to
+    1 + |q_fp64| the kernel (bf16x3: fp32 exponent range, nothing overflows) stays within 3e-4 and within 4x of what
+    the fp32 reference path itself achieves (+1e-5); fp16x3 runs out of range at x8 and says so (NaN + NONFINITE)."""
+    model, hp, sd = _model_with_precision("bf16x3", stress=stress)
+    latent, poses, cond = _inputs(128, 7)
+    ref32 = _oracle(sd, hp, latent, cond)
+    ref64 = freia_flow.flow_inverse(freia_flow.state_dict_to(sd, torch.float64), latent.double(), cond.double(), 12, 3, 2.5)[0]
+    out = model.inverse(latent.to(DEV), cond.to(DEV)).cpu()
+    rel_ref = ((ref32.double() - ref64).abs() / (1 + ref64.abs())).max().item()
+    rel = ((out.double() - ref64).abs() / (1 + ref64.abs())).max().item()
+    print("stress x%g: |q| max %.3g, abs err kernel %.3g / fp32 oracle %.3g, rel err kernel %.3g / fp32 oracle %.3g"
+          % (stress, ref64.abs().max(), (out.double() - ref64).abs().max(), (ref32.double() - ref64).abs().max(), rel, rel_ref))
+    assert torch.isfinite(out).all() and model.status() == 0
+    assert rel < 3e-4 and rel <= 4 * rel_ref + 1e-5, (rel, rel_ref)
+    if stress == 8.0:
+        model16, _, _ = _model_with_precision("fp16x3", stress=stress)
+        out16 = model16.inverse(latent.to(DEV), cond.to(DEV))
+        torch.cuda.synchronize()
+        if not torch.isfinite(out16).all():
+            assert model16.poll_status() & ikflow_b200._lib.IKF_STATUS_NONFINITE
+            assert model16.status() & ikflow_b200._lib.IKF_STATUS_NONFINITE
+
+
+def test_two_streams_and_two_threads_share_one_handle():
+    """the library is re-entrant per handle + stream.  200 calls interleaved over two streams (different
+    batches, so different kernels and sequence-number advances) and then from two host threads: every result is bitwise
+    the serial one."""
+    import threading
+
+    solver, hp, sd = _solver(12, 7, 3, 1024)
+    model = solver.nn_model
+    la, _, ca = _inputs(512, 7, seed=1)
+    lb, _, cb = _inputs(700, 7, seed=2)
+    la, ca, lb, cb = la.to(DEV), ca.to(DEV), lb.to(DEV), cb.to(DEV)
+    ref_a, ref_b = model.inverse(la, ca).clone(), model.inverse(lb, cb).clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for i in range(200):
+        with torch.cuda.stream(s1 if i % 2 == 0 else s2):
+            outs.append(model.inverse(la, ca) if i % 3 else model.inverse(lb, cb))
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs):
+        assert torch.equal(o, ref_a if i % 3 else ref_b), i
+    results = {}
+
+    def worker(name, lat, cnd, n):
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            results[name] = [model.inverse(lat, cnd) for _ in range(n)]
+        st.synchronize()
+
+    ts = [threading.Thread(target=worker, args=("a", la, ca, 60)), threading.Thread(target=worker, args=("b", lb, cb, 60))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    torch.cuda.synchronize()
+    assert all(torch.equal(o, ref_a) for o in results["a"]) and all(torch.equal(o, ref_b) for o in results["b"])
+    assert model.status() == 0
+
+
+def test_nan_inputs_propagate_like_torch_clamp_and_are_reported():
+    """``robot.clamp_to_joint_limits`` is ``torch.clamp`` per column: NaN stays NaN (fminf/fmaxf would have returned a
+    joint limit).  The status word reports it without a synchronising call."""
+    solver, hp, sd = _solver(3, 9, 2, 256)
+    latent, poses, cond = _inputs(40, 9)
+    latent[7, 2] = float("nan")
+    ref = jk.clamp_to_joint_limits(jk.PANDA, _oracle(sd, hp, latent, cond)[:, :7].clone())
+    assert torch.isnan(ref[7]).any() and not torch.isnan(ref[torch.arange(40) != 7]).any()
+    assert solver.nn_model.status() == 0
+    sol = solver.generate_ik_solutions(poses.to(DEV), latent=latent.to(DEV)).cpu()
+    assert torch.equal(torch.isnan(sol), torch.isnan(ref))
+    ok = ~torch.isnan(ref)
+    assert (sol[ok] - ref[ok]).abs().max() < TOL
+    torch.cuda.synchronize()
+    assert solver.nn_model.poll_status() & ikflow_b200._lib.IKF_STATUS_NONFINITE  # no sync needed to see it
+    assert solver.nn_model.status() & ikflow_b200._lib.IKF_STATUS_NONFINITE
+    assert solver.nn_model.status() == 0 and solver.nn_model.poll_status() == 0  # read-and-clear
+
+
+def test_last_kernel_reports_what_was_launched():
+    solver, hp, sd = _solver(12, 7, 3, 1024)
+    latent, poses, cond = _inputs(2048, 7)
+    for batch, tag in ((512, "<32,true,false>"), (1024, "<64,false,false>"), (2048, "<128,false,false>")):
+        solver.nn_model.inverse(latent[:batch].to(DEV), cond[:batch].to(DEV))
+        assert solver.nn_model.last_kernel().endswith("flow_inverse_umma_kernel" + tag), solver.nn_model.last_kernel()

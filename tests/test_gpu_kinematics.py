@@ -172,3 +172,53 @@ def test_lm_refine_matches_reference_loop_semantics(panda, r):
 def test_empty_batches_are_noops(panda):
     assert panda.forward_kinematics(torch.zeros(0, 7, device=DEV)).shape == (0, 7)
     assert panda.inverse_kinematics_step_levenburg_marquardt(torch.zeros(0, 7, device=DEV), torch.zeros(0, 7, device=DEV)).shape == (0, 7)
+
+
+# ---- round 2: device-side target-pose generator, NaN semantics of the clamp -----------------------------
+@pytest.mark.parametrize("robot_name", ["panda", "fetch_arm"])
+def test_pose_sampler_matches_oracle_fed_the_same_uniforms(robot_name):
+    """``Robot.sample_joint_angles_and_poses`` = ONE launch (Philox4x32-10 draw + FK).  Parity: joint angles bit-equal to
+    the oracle's sampler map fed the uniforms of the oracle's Philox restatement (pinned by the Random123 KATs); poses
+    equal to the oracle FK of those angles."""
+    from oracle.philox import sample_uniforms
+
+    robot = ikflow_b200.get_robot(robot_name)
+    chain = jk.ROBOTS[robot_name]
+    n, seed = 5000, 0x1234_5678_9ABC_DEF0
+    from ikflow_b200 import _lib
+
+    launches = _lib.launch_count()
+    q, poses = robot.sample_joint_angles_and_poses(n, seed=seed, return_torch=True, device=DEV)
+    assert _lib.launch_count() - launches == 1
+    assert q.is_cuda and poses.is_cuda and q.shape == (n, robot.ndof) and poses.shape == (n, 7)
+    u = torch.from_numpy(sample_uniforms(seed, 0, n, robot.ndof))
+    q_ref = jk.joint_angles_from_uniforms(chain, u, 1e-6)
+    assert torch.equal(q.cpu(), q_ref)
+    ref_poses = jk.forward_kinematics(chain, q_ref)
+    assert (poses.cpu()[:, :3] - ref_poses[:, :3]).abs().max() < 2e-6
+    assert _quat_close(poses.cpu()[:, 3:], ref_poses[:, 3:], 2e-6)
+    lims = torch.tensor(chain.actuated_joints_limits)
+    assert (q.cpu() > lims[:, 0]).all() and (q.cpu() < lims[:, 1]).all()
+    # shards of one stream: any split of the index range reproduces it (multi-GPU pose generation needs no exchange)
+    q2, p2 = robot.sample_joint_angles_and_poses(1000, seed=seed, first_index=3000, return_torch=True, device=DEV)
+    assert torch.equal(q2, q[3000:4000]) and torch.equal(p2, poses[3000:4000])
+    # numpy return type of jrl, seeding through torch's generator, other eps
+    torch.manual_seed(5)
+    a = robot.sample_joint_angles_and_poses(64)
+    torch.manual_seed(5)
+    b = robot.sample_joint_angles_and_poses(64)
+    assert isinstance(a[0], np.ndarray) and a[0].shape == (64, robot.ndof) and a[1].shape == (64, 7)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    q3, _ = robot.sample_joint_angles_and_poses(256, joint_limit_eps=0.1, seed=3, return_torch=True, device=DEV)
+    assert torch.equal(q3.cpu(), jk.joint_angles_from_uniforms(chain, torch.from_numpy(sample_uniforms(3, 0, 256, robot.ndof)), 0.1))
+    assert robot.sample_joint_angles_and_poses(0, seed=1, return_torch=True, device=DEV)[0].shape == (0, robot.ndof)
+
+
+def test_clamp_propagates_nan_like_torch_clamp(panda):
+    q = torch.zeros(9, 7)
+    q[3, 1] = float("nan")
+    q[4, 6] = 50.0
+    ref = jk.clamp_to_joint_limits(jk.PANDA, q.clone())
+    got = panda.clamp_to_joint_limits(q.to(DEV)).cpu()
+    assert torch.isnan(got[3, 1]) and torch.isnan(ref[3, 1])
+    assert torch.equal(torch.nan_to_num(got, nan=123.0), torch.nan_to_num(ref, nan=123.0))

@@ -231,3 +231,22 @@ def test_oracle_reproduces_reference_exact_fixture_scenario_b():
     assert torch.equal(valids, torch.from_numpy(d["b_valids"]))
     assert torch.equal(sols, torch.from_numpy(d["b_solutions"]))
     assert int(valids.sum()) == 1966 and len(log) == 3 and log[2][0][0] % 10 == 0  # the r = 10 pass ran
+
+
+def test_philox4x32_10_known_answer_vectors():
+    """Random123 kat_vectors (philox4x32, 10 rounds): zero, all-ones and the pi-digit counter/key."""
+    from oracle.philox import philox4x32_10, sample_uniforms
+
+    u32 = lambda *a: np.array(a, dtype=np.uint32)
+    assert philox4x32_10(u32(0, 0, 0, 0), u32(0, 0)).tolist() == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    ones = 0xFFFFFFFF
+    assert philox4x32_10(u32(ones, ones, ones, ones), u32(ones, ones)).tolist() == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert philox4x32_10(u32(0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), u32(0xA4093822, 0x299F31D0)).tolist() == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+    u = sample_uniforms(seed=7, first_index=0, n=20000, ndof=7)
+    assert u.shape == (20000, 7) and 0.0 < u.min() and u.max() < 1.0
+    assert np.abs(u.mean(0) - 0.5).max() < 0.01 and np.abs(np.corrcoef(u.T) - np.eye(7)).max() < 0.03
+    # a sample depends on (seed, index) only: any split of the index range gives the same stream
+    assert np.array_equal(sample_uniforms(7, 1000, 50, 7), u[1000:1050])
+    q = jk.joint_angles_from_uniforms(jk.PANDA, torch.from_numpy(u))
+    lims = torch.tensor(jk.PANDA.actuated_joints_limits)
+    assert (q >= lims[:, 0]).all() and (q <= lims[:, 1]).all()
