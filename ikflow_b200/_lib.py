@@ -48,6 +48,7 @@ PROTOTYPES = {
     "ikf_flow_status": (c_int, [c_void_p, c_void_p, POINTER(c_uint32)]),
     "ikf_flow_poll_status": (c_int, [c_void_p, POINTER(c_uint32)]),
     "ikf_flow_last_kernel": (c_char_p, [c_void_p]),
+    "ikf_flow_last_cluster": (c_int, [c_void_p]),
     "ikf_flow_debug_trace": (c_int, [c_void_p, c_void_p, c_int]),
     "ikf_flow_info": (c_int, [c_void_p, POINTER(c_size_t), POINTER(c_int), POINTER(c_int)]),
     "ikf_robot_create": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(c_void_p)]),

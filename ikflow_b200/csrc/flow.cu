@@ -82,6 +82,8 @@ static size_t subnet_weight_count(const IkfFlowDesc* d, int in_dim, int out_dim)
 
 }  // namespace ikf
 
+constexpr int kDefaultCluster = 1;
+
 struct IkfFlow {
   IkfFlowDesc desc;
   int device = 0;
@@ -96,7 +98,7 @@ struct IkfFlow {
   bool jit = false;  // umma engine, 32-row groups: first layer computed just in time by every CTA (flow_umma.cuh)
   int engine = 0;  // 0 = mma.sync tiles (flow_mma.cuh), 1 = tcgen05 / TMEM (flow_umma.cuh)
   uint32_t epoch = 1;  // doubles as launch id; 0 is "no launch aborted"
-  int last_grid = 0;
+  int last_grid = 0, last_cluster = 1;
   unsigned long long* trace = nullptr;
   int trace_layers = 0;
   size_t smem_bytes = 0;
@@ -122,7 +124,11 @@ struct IkfFlow {
     int threads = 0;
     size_t smem = 0;
     const char* name = "";
+    int max_slots_cs[5] = {0, 0, 0, 0, 0};  // [cs]: team slots that are co-resident when launched in clusters of cs CTAs (cs = 2, 4)
   } kern[4];
+  // tcgen05 engine: CTAs per cluster for the weight multicast across teams (1 = off); IKFLOW_B200_CLUSTER overrides
+  int cluster_pref = kDefaultCluster;
+  bool cluster_ok = true;  // cleared if the driver refuses a cooperative launch with clusters
 };
 
 using namespace ikf;
@@ -456,6 +462,33 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
     }
     f->slots_max = std::max(1, occ * f->num_sms / NT);
   }
+  if (const char* env = std::getenv("IKFLOW_B200_CLUSTER")) {
+    const int v = std::atoi(env);
+    if (v == 1 || v == 2 || v == 4) f->cluster_pref = v;
+  }
+  if (e == cudaSuccess && engine && f->cluster_pref > 1) {
+    // how many clusters of cs CTAs the device holds at once (clusters are placed inside a GPC, so this is not num_sms / cs)
+    for (IkfFlow::Kernel& k : f->kern) {
+      if (!k.fn) continue;
+      for (int cs = 2; cs <= 4; cs *= 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cs * NT);
+        cfg.blockDim = dim3(k.threads);
+        cfg.dynamicSmemBytes = k.smem;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = cs, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, k.fn, &cfg) != cudaSuccess) {
+          cudaGetLastError();
+          n_clusters = 0;
+        }
+        k.max_slots_cs[cs] = (n_clusters * cs / NT) / cs * cs;  // whole groups of cs teams
+      }
+    }
+  }
   if (e != cudaSuccess) {
     ikf_flow_destroy(f);
     return fail(IKF_ECUDA, "ikf_flow_create: device setup failed: %s", cudaGetErrorString(e));
@@ -537,6 +570,19 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   if (flow->forced_rt) rt = flow->forced_rt;
   p.n_rowgroups = (batch + rt - 1) / rt;
   p.slots = std::min(p.n_rowgroups, flow->slots_max);
+  const IkfFlow::Kernel& k = flow->kern[(rt == 32 && flow->jit) ? 3 : rt == 32 ? 0 : rt == 64 ? 1 : 2];
+  // Clusters of cs CTAs = the CTAs with the same feature tile of cs neighbouring teams share every weight chunk by
+  // multicast (FlowParams::cluster).  Needs cs teams at least; the slot count becomes a multiple of cs (surplus teams
+  // walk empty row groups).
+  int cs = 1;
+  if (flow->engine && flow->cluster_ok)
+    for (int c = flow->cluster_pref; c > 1; c >>= 1)
+      if (p.n_rowgroups >= c && k.max_slots_cs[c] >= c) {
+        cs = c;
+        break;
+      }
+  if (cs > 1) p.slots = std::min((p.n_rowgroups + cs - 1) / cs * cs, k.max_slots_cs[cs]);
+  p.cluster = cs;
   p.epoch = flow->epoch;
   p.trace = flow->trace;
   p.trace_layers = flow->trace_layers;
@@ -547,10 +593,10 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
 
   const int grid = p.slots * flow->NT;
   flow->last_grid = grid;
+  flow->last_cluster = cs;
   void* args[] = {(void*)&p};
   // cooperative launch = the driver guarantees that all CTAs of all teams are co-resident (the teams spin on each
   // other's flags)
-  const IkfFlow::Kernel& k = flow->kern[(rt == 32 && flow->jit) ? 3 : rt == 32 ? 0 : rt == 64 ? 1 : 2];
   const void* fn = k.fn;
   const int threads = k.threads;
   const size_t smem = k.smem;
@@ -564,7 +610,35 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
     cudaError_t we = cudaStreamWaitEvent(st, flow->done, 0);
     if (we != cudaSuccess) return fail(IKF_ECUDA, "%s: cudaStreamWaitEvent failed: %s", name, cudaGetErrorString(we));
   }
-  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, st);
+  cudaError_t e;
+  if (cs > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeCooperative;
+    attrs[0].val.cooperative = 1;
+    attrs[1].id = cudaLaunchAttributeClusterDimension;
+    attrs[1].val.clusterDim.x = cs, attrs[1].val.clusterDim.y = 1, attrs[1].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 2;
+    e = cudaLaunchKernelExC(&cfg, fn, args);
+    if (e != cudaSuccess) {
+      // the driver will not place this grid in clusters: remember it and fall back to the plain launch (nothing ran)
+      cudaGetLastError();
+      flow->cluster_ok = false;
+      last_error_ref() = std::string("cluster launch refused (") + cudaGetErrorString(e) + "), clusters disabled for this handle";
+      p.cluster = 1;
+      p.slots = std::min(p.n_rowgroups, flow->slots_max);
+      flow->last_cluster = 1;
+      flow->last_grid = p.slots * flow->NT;
+      e = cudaLaunchCooperativeKernel(fn, dim3(p.slots * flow->NT), dim3(threads), args, smem, st);
+    }
+  } else {
+    e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, st);
+  }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return fail(IKF_ECUDA, "%s: launch failed: %s", name, cudaGetErrorString(e));
   if (capturing == cudaStreamCaptureStatusNone) {
@@ -639,6 +713,8 @@ int ikf_flow_debug_trace(IkfFlow* flow, unsigned long long* dev_stamps, int n_la
 }
 
 const char* ikf_flow_last_kernel(IkfFlow* flow) { return flow ? flow->last_kernel : ""; }
+
+int ikf_flow_last_cluster(IkfFlow* flow) { return flow ? flow->last_cluster : IKF_EINVAL; }
 
 int ikf_flow_info(IkfFlow* flow, size_t* packed_weight_bytes, int* grid_ctas_last, int* smem_bytes) {
   if (!flow) return fail(IKF_EINVAL, "ikf_flow_info: flow is NULL");

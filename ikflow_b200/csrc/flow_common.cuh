@@ -70,6 +70,11 @@ struct FlowParams {
   float* out;
   int in_ld, cond_ld, cond_rows, cond_cols, out_ld, out_cols;
   int batch, block_first, block_last, finalize, clamp_out, n_rowgroups, slots;
+  // tcgen05 engine: CTAs per thread-block cluster (1 = no clusters).  A cluster holds the CTAs with the SAME feature tile
+  // t of `cluster` neighbouring teams: they need the same weight chunks at the same time, so each loads 1/cluster of a
+  // chunk and multicasts it to all of them (one L2 read instead of `cluster`).  CTA -> (team slot, feature tile t):
+  //   c = blockIdx.x / cluster, r = blockIdx.x % cluster (= %cluster_ctarank), t = c % NT, slot = (c / NT) * cluster + r
+  int cluster;
   int forward;         // 1: x -> z with log-det (blocks block_last..block_first ascending), tcgen05 engine only
   float logdet_m;      // FixedLinearTransform.logDetM
   float* logdet_out;   // [batch] (forward pass)
@@ -134,6 +139,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
                    smem_u32(dst_smem)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// The same copy delivered to the same shared-memory offset of every CTA of the cluster named in `cta_mask`; each
+// destination's mbarrier (same offset) receives the complete_tx.
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)),
@@ -224,18 +241,36 @@ __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t expecte
   }
 }
 
+__device__ __forceinline__ void cta_coords(const FlowParams& p, int& slot, int& t) {
+  const int cs = p.cluster > 1 ? p.cluster : 1;
+  const int c = blockIdx.x / cs, r = blockIdx.x % cs;
+  t = c % p.NT;
+  slot = (c / p.NT) * cs + r;
+}
+// index of this CTA inside team 0 (the team the debug trace follows), or -1
+__device__ __forceinline__ int trace_cta(const FlowParams& p) {
+  int slot, t;
+  cta_coords(p, slot, t);
+  return slot == 0 ? t : -1;
+}
+
 constexpr int kTraceEvents = 96;  // stamps per (CTA, layer): 0-15 phase events; per k-chunk i: 16+i landed (MMA warp), 32+i stage free
                                   // (loader), 48+i copies issued, 64+i expect_tx done, 80+i weight copy issued
 // per-chunk stamps (events 16..63) use the SM clock: cheap to read, only compared inside one CTA
 __device__ __forceinline__ void trace_clk(const FlowParams& p, int layer, int ev) {
-  if (p.trace != nullptr && (p.debug & 4) && blockIdx.x < p.NT && layer < p.trace_layers)  // IKFLOW_B200_DEBUG=4: they perturb
-    p.trace[((size_t)blockIdx.x * p.trace_layers + layer) * kTraceEvents + ev] = (unsigned long long)clock64();
+  if (p.trace != nullptr && (p.debug & 4) && layer < p.trace_layers) {  // IKFLOW_B200_DEBUG=4: they perturb
+    const int tc = trace_cta(p);
+    if (tc >= 0) p.trace[((size_t)tc * p.trace_layers + layer) * kTraceEvents + ev] = (unsigned long long)clock64();
+  }
 }
 __device__ __forceinline__ void trace_ev(const FlowParams& p, int layer, int ev) {
-  if (p.trace != nullptr && blockIdx.x < p.NT && layer < p.trace_layers) {
-    unsigned long long tns;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
-    p.trace[((size_t)blockIdx.x * p.trace_layers + layer) * kTraceEvents + ev] = tns;
+  if (p.trace != nullptr && layer < p.trace_layers) {
+    const int tc = trace_cta(p);
+    if (tc >= 0) {
+      unsigned long long tns;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tns));
+      p.trace[((size_t)tc * p.trace_layers + layer) * kTraceEvents + ev] = tns;
+    }
   }
 }
 

@@ -229,6 +229,12 @@ __device__ __forceinline__ void mma_chunk_x1(uint32_t tmem_d, uint32_t idesc, ui
       "r"(idesc), "l"(wh), "l"(ah), "r"(acc_first)
       : "memory");
 }
+// ... and on the barrier at the same offset in every CTA of the cluster named in `cta_mask`
+__device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -412,14 +418,17 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
   const int lane = tid & 31;
   const int NT = p.NT;            // hidden / 128
   const int KCH = p.H / kKC;      // 64-wide k-chunks per hidden layer (2 per producer)
-  const int slot = blockIdx.x / NT;
-  const int t = blockIdx.x % NT;
+  int slot, t;
+  cta_coords(p, slot, t);
+  // CTAs per cluster: same t, neighbouring teams (FlowParams::cluster).  Read from the parameter bank where needed
+  // (the kernel is at its register limit: no function-scope copies).
+#define IKF_CS (p.cluster > 1 ? p.cluster : 1)
   const uint32_t launch_id = p.epoch;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&sm.full[s], C::kFullCount);
-      mbar_init(&sm.empty[s], 1);
+      mbar_init(&sm.empty[s], IKF_CS);  // clusters: a stage is refilled by multicast, so it must be free in EVERY CTA of the cluster
       mbar_init(&sm.w1full[s], 1);
       mbar_init(&sm.w1empty[s], 1);
     }
@@ -440,6 +449,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();  // the peers' barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
@@ -449,7 +459,9 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
 
   const int n_blocks = p.block_first - p.block_last + 1;
   const int steps_per_rg = 2 * n_blocks;
-  const int my_rgs = (p.n_rowgroups - slot + p.slots - 1) / p.slots;
+  // clusters keep their CTAs in lock step (the weight stream is shared): every team then walks the same number of row
+  // groups, the last ones possibly empty (rows >= batch read as zeros and are not written)
+  const int my_rgs = p.cluster > 1 ? (p.n_rowgroups + p.slots - 1) / p.slots : (p.n_rowgroups - slot + p.slots - 1) / p.slots;
   const int total_steps = my_rgs * steps_per_rg;
 
   // Just-in-time first layer of subnet step g: generation warp j (epilogue warps 0-3, helper warps 4-7) runs over the
@@ -475,8 +487,8 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
     // the (busy) shared memory
     // cheap per-chunk stamps (IKFLOW_B200_DEBUG=4): row 4g+2 (group 0) / 4g+3... of the trace, SM clock
     unsigned long long* tb = nullptr;
-    if (p.trace != nullptr && (p.debug & 4) && blockIdx.x < p.NT && g * 4 + 2 < p.trace_layers && j == 0 && lane == 0)
-      tb = p.trace + ((size_t)blockIdx.x * p.trace_layers + g * 4 + 2) * kTraceEvents + grp * 8;
+    if (p.trace != nullptr && (p.debug & 4) && slot == 0 && g * 4 + 2 < p.trace_layers && j == 0 && lane == 0)
+      tb = p.trace + ((size_t)t * p.trace_layers + g * 4 + 2) * kTraceEvents + grp * 8;
     for (int i = grp; i < KCH; i += 2) {
       const int st = i % kStages;  // every layer starts at ring stage 0 (KCH % kStages == 0, checked at launch)
       const uint32_t stage_a = smem_u32(sm.ring[st]);
@@ -617,7 +629,15 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
           } else {
             if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], (p.debug & 1 ? 0 : C::kAChunk) + (p.debug & 2 ? 0 : kWChunkU));
           }
-          if (lane < (a_now ? 2 : 1) && !((p.debug >> (1 - lane)) & 1)) bulk_g2s(my_dst, my_src, my_bytes, my_bar);
+          if (p.cluster > 1 && lane == 0) {
+            // this CTA's share of the weight chunk, delivered to every CTA of the cluster (all of them wait for the same
+            // chunk in the same ring stage; the `empty` barrier above has told us that the stage is free in all of them)
+            const uint32_t share = (uint32_t)kWChunkU / (uint32_t)p.cluster;
+            const uint32_t off = (blockIdx.x % (uint32_t)p.cluster) * share;
+            bulk_g2s_multicast(my_dst + off, (const uint8_t*)my_src + off, share, my_bar, (uint16_t)((1u << p.cluster) - 1u));
+          } else if (lane < (a_now ? 2 : 1) && !((p.debug >> (1 - lane)) & 1)) {
+            bulk_g2s(my_dst, my_src, my_bytes, my_bar);
+          }
           __syncwarp();
           if (!prefetched) {  // after this warp's first copies of the layer are on their way
             prefetched = true;
@@ -712,7 +732,8 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
                     mma_chunk_x3(tmem_u, tmem_u2, idesc2, idesc, d_wh0 + s * kStageOff, d_wl0 + s * kStageOff, d_a0 + s * kStageOff, (i0 + s) != 0);
                   else
                     mma_chunk_x1(tmem_u, idesc, d_wh0 + s * kStageOff, d_a0 + s * kStageOff, (i0 + s) != 0);
-                  mma_commit(&sm.empty[s]);  // the stage is free once these MMAs have read it
+                  // the stage is free once these MMAs have read it (clusters: tell every CTA that refills it)
+                  if (p.cluster > 1) mma_commit_multicast(&sm.empty[s], (uint16_t)((1u << p.cluster) - 1u)); else mma_commit(&sm.empty[s]);
                 }
                 __syncwarp();
               }
@@ -730,7 +751,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
                   mma_chunk_x3(tmem_u, tmem_u2, idesc2, idesc, d_wh0 + soff, d_wl0 + soff, d_a0 + soff, i != 0);
                 else
                   mma_chunk_x1(tmem_u, idesc, d_wh0 + soff, d_a0 + soff, i != 0);
-                mma_commit(&sm.empty[s]);
+                if (p.cluster > 1) mma_commit_multicast(&sm.empty[s], (uint16_t)((1u << p.cluster) - 1u)); else mma_commit(&sm.empty[s]);
               }
               __syncwarp();
               ++ring_pos;
@@ -781,7 +802,8 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
     };
 
     int g = 0;
-    for (int rg = slot; rg < p.n_rowgroups; rg += p.slots) {
+    for (int rgi = 0; rgi < my_rgs; ++rgi) {
+      const int rg = slot + rgi * p.slots;  // >= n_rowgroups: an empty row group of a cluster in lock step
       for (int i = tid; i < RT * kPad; i += ET) {
         const int r = i / kPad, j = i % kPad;
         const int row = rg * RT + r;
@@ -1163,10 +1185,13 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
 
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == C::kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(C::kTmemCols) : "memory");
   }
 }
+
+#undef IKF_CS
 
 }  // namespace umma
 }  // namespace ikf

@@ -224,6 +224,10 @@ class FlowModel:
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         return _lib.lib().ikf_flow_last_kernel(self._handle(dev)).decode()
 
+    def last_cluster(self, device=None) -> int:
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        return int(_lib.lib().ikf_flow_last_cluster(self._handle(dev)))
+
     def info(self, device=None) -> Dict[str, int]:
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         nbytes, grid, smem = ctypes.c_size_t(0), ctypes.c_int(0), ctypes.c_int(0)

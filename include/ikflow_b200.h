@@ -146,6 +146,9 @@ int ikf_flow_poll_status(IkfFlow* flow, uint32_t* status_out);
 
 /* Name of the kernel the last launch on this handle used (for benchmark / profile bookkeeping). */
 const char* ikf_flow_last_kernel(IkfFlow* flow);
+/* CTAs per thread-block cluster of the last launch (1 = no clusters): the CTAs holding the same weight slice of
+ * neighbouring teams load every weight chunk once and multicast it (IKFLOW_B200_CLUSTER=1|2|4 overrides the default). */
+int ikf_flow_last_cluster(IkfFlow* flow);
 
 /* Introspection for benchmarks: bytes of packed weights resident in HBM, CTAs per launch, dynamic smem per CTA. */
 int ikf_flow_info(IkfFlow* flow, size_t* packed_weight_bytes, int* grid_ctas_last, int* smem_bytes);

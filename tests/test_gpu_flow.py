@@ -488,3 +488,31 @@ def test_last_kernel_reports_what_was_launched():
     for batch, tag in ((512, "<32,true,false>"), (1024, "<64,false,false>"), (2048, "<128,false,false>")):
         solver.nn_model.inverse(latent[:batch].to(DEV), cond[:batch].to(DEV))
         assert solver.nn_model.last_kernel().endswith("flow_inverse_umma_kernel" + tag), solver.nn_model.last_kernel()
+
+
+@pytest.mark.parametrize("cluster", ["2", "4"])
+@pytest.mark.parametrize("rt,batch", [("32", 512), ("32", 100), ("32", 1500), ("64", 1000), ("128", 2048), ("128", 300)])
+def test_weight_multicast_clusters_are_bitwise_identical_to_unclustered_launches(cluster, rt, batch, monkeypatch):
+    """IKFLOW_B200_CLUSTER = 2 / 4: the CTAs that hold the same weight slice in neighbouring teams form a cluster, each
+    loads 1/cs of every weight chunk and multicasts it.  Only the way the weights reach shared memory changes: results
+    must be bit-identical to the unclustered launch -- including batches whose row-group count is not a multiple of the
+    cluster size (surplus teams walk empty row groups) and several row groups per team."""
+    hp = IkflowModelParameters()
+    hp.nb_nodes, hp.dim_latent_space = 4, 7
+    robot = ikflow_b200.Panda()
+    sd = make_synthetic_state_dict(hp, robot.actuated_joints_limits, seed=0)
+    latent, poses, cond = _inputs(batch, 7)
+    outs = []
+    for cs in ("1", cluster):
+        monkeypatch.setenv("IKFLOW_B200_CLUSTER", cs)
+        monkeypatch.setenv("IKFLOW_B200_RT", rt)
+        model = ikflow_b200.glow_cNF_model(hp, robot, 8, 7)
+        model.load_state_dict(sd)
+        outs.append(model.inverse(latent.to(DEV), cond.to(DEV)).clone())
+        again = model.inverse(latent.to(DEV), cond.to(DEV))
+        assert torch.equal(again, outs[-1])
+        assert model.status() == 0
+        n_groups = -(-batch // int(rt))
+        assert model.last_cluster() == (int(cs) if n_groups >= int(cs) else (2 if cs == "4" and n_groups >= 2 else 1)), (model.last_cluster(), cs)
+    assert torch.equal(outs[0], outs[1])
+    assert (outs[0].cpu() - _oracle(sd, hp, latent, cond)).abs().max() < TOL
