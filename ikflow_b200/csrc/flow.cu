@@ -82,7 +82,12 @@ static size_t subnet_weight_count(const IkfFlowDesc* d, int in_dim, int out_dim)
 
 }  // namespace ikf
 
-constexpr int kDefaultCluster = 1;
+// Default cluster size of the weight multicast: measured on B200 (scripts/time_flow.py, same box) clusters of 2 gain
+// 3-6 % wherever the weight stream paces the hidden layers (64- / 128-row groups, exchanged first layer) and cost 1.5 %
+// in the just-in-time kernel of the 512-pose headline (its hidden layers are paced by the SIMT generation of the
+// operand, and the lock step of the two teams only adds jitter); clusters of 4 are never better than 2.
+constexpr int kDefaultCluster = 2;
+constexpr int kDefaultClusterJit = 1;
 
 struct IkfFlow {
   IkfFlowDesc desc;
@@ -127,7 +132,7 @@ struct IkfFlow {
     int max_slots_cs[5] = {0, 0, 0, 0, 0};  // [cs]: team slots that are co-resident when launched in clusters of cs CTAs (cs = 2, 4)
   } kern[4];
   // tcgen05 engine: CTAs per cluster for the weight multicast across teams (1 = off); IKFLOW_B200_CLUSTER overrides
-  int cluster_pref = kDefaultCluster;
+  int cluster_pref = kDefaultCluster, cluster_pref_jit = kDefaultClusterJit;
   bool cluster_ok = true;  // cleared if the driver refuses a cooperative launch with clusters
 };
 
@@ -464,9 +469,9 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   }
   if (const char* env = std::getenv("IKFLOW_B200_CLUSTER")) {
     const int v = std::atoi(env);
-    if (v == 1 || v == 2 || v == 4) f->cluster_pref = v;
+    if (v == 1 || v == 2 || v == 4) f->cluster_pref = f->cluster_pref_jit = v;
   }
-  if (e == cudaSuccess && engine && f->cluster_pref > 1) {
+  if (e == cudaSuccess && engine && std::max(f->cluster_pref, f->cluster_pref_jit) > 1) {
     // how many clusters of cs CTAs the device holds at once (clusters are placed inside a GPC, so this is not num_sms / cs)
     for (IkfFlow::Kernel& k : f->kern) {
       if (!k.fn) continue;
@@ -576,7 +581,7 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   // walk empty row groups).
   int cs = 1;
   if (flow->engine && flow->cluster_ok)
-    for (int c = flow->cluster_pref; c > 1; c >>= 1)
+    for (int c = (&k == &flow->kern[3]) ? flow->cluster_pref_jit : flow->cluster_pref; c > 1; c >>= 1)
       if (p.n_rowgroups >= c && k.max_slots_cs[c] >= c) {
         cs = c;
         break;
