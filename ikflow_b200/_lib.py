@@ -44,6 +44,8 @@ PROTOTYPES = {
     "ikf_flow_inverse": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ikf_flow_inverse_blocks": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ikf_flow_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "ikf_flow_set_peers": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "ikf_flow_inverse_gather": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_size_t, c_int, c_int, c_void_p]),
     "ikf_flow_set_forward_tables": (c_int, [c_void_p, c_void_p, c_float]),
     "ikf_flow_status": (c_int, [c_void_p, c_void_p, POINTER(c_uint32)]),
     "ikf_flow_poll_status": (c_int, [c_void_p, POINTER(c_uint32)]),

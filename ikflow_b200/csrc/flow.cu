@@ -132,6 +132,11 @@ struct IkfFlow {
     int max_slots_cs[5] = {0, 0, 0, 0, 0};  // [cs]: team slots that are co-resident when launched in clusters of cs CTAs (cs = 2, 4)
   } kern[4];
   // tcgen05 engine: CTAs per cluster for the weight multicast across teams (1 = off); IKFLOW_B200_CLUSTER overrides
+  // fused gather (ikf_flow_set_peers): peer-mapped gathered buffers / flag arrays of every rank of the node
+  int n_ranks = 0, rank = 0;
+  float* peer_out[ikf::kMaxPeers] = {};
+  uint32_t* peer_flag[ikf::kMaxPeers] = {};
+  uint32_t peer_seq = 0, peer_count_total = 0;
   int cluster_pref = kDefaultCluster, cluster_pref_jit = kDefaultClusterJit;
   bool cluster_ok = true;  // cleared if the driver refuses a cooperative launch with clusters
 };
@@ -392,7 +397,7 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   const size_t off_partial = align_up(off_act + act_bytes);
   const size_t partial_bytes = (size_t)slots * 2 * NT * (engine ? umma::kRTMaxU * umma::kPartRowBytes : kRTMax * kPad * 4);
   const size_t off_flags = align_up(off_partial + partial_bytes);
-  const size_t flag_bytes = ((size_t)slots * 2 * NT * 2 + 2) * 4;
+  const size_t flag_bytes = ((size_t)slots * 2 * NT * 2 + 2 + 2) * 4;  // + status [2] + fused-gather counter [2]
   f->blob_bytes = align_up(off_flags + flag_bytes);
   f->big_w_bytes = big_elems * 2;
   cudaError_t e = cudaMalloc(&f->blob, f->blob_bytes);
@@ -520,6 +525,7 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   p.act_flag = (uint32_t*)(base + off_flags);
   p.part_flag = p.act_flag + (size_t)slots * 2 * NT;
   p.status = p.part_flag + (size_t)slots * 2 * NT;
+  p.peer_counter = p.status + 2;
   {
     void* dev_view = nullptr;
     e = cudaHostGetDevicePointer(&dev_view, (void*)f->status_host, 0);
@@ -533,9 +539,17 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   return IKF_OK;
 }
 
+// fused gather of one launch: offset (floats) of the gathered buffer inside every rank's symmetric allocation, its row
+// stride, and the first row of this rank's shard
+struct GatherArgs {
+  size_t offset;
+  int ld, row0;
+};
+
 static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* cond, int cond_ld, int cond_rows,
                        int cond_cols, float* out, int out_ld, int out_cols, int batch, int block_first, int block_last,
-                       int finalize, int clamp, void* stream, const char* name, int forward = 0, float* logdet_out = nullptr) {
+                       int finalize, int clamp, void* stream, const char* name, int forward = 0, float* logdet_out = nullptr,
+                       const GatherArgs* gather = nullptr) {
   if (!flow) return fail(IKF_EINVAL, "%s: flow is NULL", name);
   if (batch < 0) return fail(IKF_EINVAL, "%s: negative batch %d", name, batch);
   if (batch == 0) return IKF_OK;
@@ -588,6 +602,20 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
       }
   if (cs > 1) p.slots = std::min((p.n_rowgroups + cs - 1) / cs * cs, k.max_slots_cs[cs]);
   p.cluster = cs;
+  p.n_peers = 0;
+  if (gather) {
+    p.n_peers = flow->n_ranks;
+    p.peer_rank = flow->rank;
+    p.peer_row0 = gather->row0;
+    p.peer_ld = gather->ld;
+    for (int r = 0; r < flow->n_ranks; ++r) {
+      p.peer_out[r] = flow->peer_out[r] + gather->offset;
+      p.peer_flag[r] = flow->peer_flag[r];
+    }
+    p.peer_seq = ++flow->peer_seq;
+    flow->peer_count_total += (uint32_t)p.slots;  // one writer CTA (t = 0) per team slot
+    p.peer_count_target = flow->peer_count_total;
+  }
   p.epoch = flow->epoch;
   p.trace = flow->trace;
   p.trace_layers = flow->trace_layers;
@@ -636,7 +664,12 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
       flow->cluster_ok = false;
       last_error_ref() = std::string("cluster launch refused (") + cudaGetErrorString(e) + "), clusters disabled for this handle";
       p.cluster = 1;
+      if (gather) flow->peer_count_total -= (uint32_t)p.slots;
       p.slots = std::min(p.n_rowgroups, flow->slots_max);
+      if (gather) {
+        flow->peer_count_total += (uint32_t)p.slots;
+        p.peer_count_target = flow->peer_count_total;
+      }
       flow->last_cluster = 1;
       flow->last_grid = p.slots * flow->NT;
       e = cudaLaunchCooperativeKernel(fn, dim3(p.slots * flow->NT), dim3(threads), args, smem, st);
@@ -646,6 +679,13 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return fail(IKF_ECUDA, "%s: launch failed: %s", name, cudaGetErrorString(e));
+  if (gather) {
+    // consumer side of the fused gather: stream-ordered wait for the shards of all ranks (one warp polling flags)
+    umma::wait_peers_kernel<<<1, 32, 0, st>>>(flow->peer_flag[flow->rank], flow->n_ranks, p.peer_seq, p.status, p.status_host);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(IKF_ECUDA, "%s: wait_peers launch failed: %s", name, cudaGetErrorString(e));
+  }
   if (capturing == cudaStreamCaptureStatusNone) {
     e = cudaEventRecord(flow->done, st);
     if (e != cudaSuccess) return fail(IKF_ECUDA, "%s: cudaEventRecord failed: %s", name, cudaGetErrorString(e));
@@ -675,6 +715,40 @@ int ikf_flow_forward(IkfFlow* flow, const float* x, int x_ld, const float* cond,
   if (!flow) return fail(IKF_EINVAL, "ikf_flow_forward: flow is NULL");
   return flow_launch(flow, x, x_ld, cond, cond_ld, cond_rows, cond_cols, z_out, out_ld, flow->desc.ndim_tot, batch,
                      flow->desc.nb_nodes - 1, 0, 0, 0, stream, "ikf_flow_forward", 1, logdet_out);
+}
+
+int ikf_flow_set_peers(IkfFlow* flow, int n_ranks, int rank, void* const* gather_bufs, void* const* flag_bufs) {
+  if (!flow) return fail(IKF_EINVAL, "ikf_flow_set_peers: flow is NULL");
+  std::lock_guard<std::mutex> lock(flow->mu);
+  if (n_ranks == 0) {  // switch the fused gather off
+    flow->n_ranks = 0;
+    return IKF_OK;
+  }
+  if (!flow->engine) return fail(IKF_EINVAL, "ikf_flow_set_peers: the fused gather is implemented by the tcgen05 engine only");
+  if (n_ranks < 1 || n_ranks > kMaxPeers || rank < 0 || rank >= n_ranks || !gather_bufs || !flag_bufs)
+    return fail(IKF_EINVAL, "ikf_flow_set_peers: need 1 <= n_ranks <= %d, 0 <= rank < n_ranks and both pointer tables", kMaxPeers);
+  for (int r = 0; r < n_ranks; ++r) {
+    if (!gather_bufs[r] || !flag_bufs[r]) return fail(IKF_EINVAL, "ikf_flow_set_peers: NULL pointer for rank %d", r);
+    flow->peer_out[r] = (float*)gather_bufs[r];
+    flow->peer_flag[r] = (uint32_t*)flag_bufs[r];
+  }
+  flow->n_ranks = n_ranks;
+  flow->rank = rank;
+  flow->peer_seq = 0;  // the flag arrays start zeroed on every rank (the caller's job, before its barrier)
+  return IKF_OK;
+}
+
+int ikf_flow_inverse_gather(IkfFlow* flow, const float* latent, int latent_ld, const float* cond, int cond_ld, int cond_rows,
+                            int cond_cols, int out_cols, int batch, int clamp, size_t gather_offset, int gather_ld, int row0,
+                            void* stream) {
+  if (!flow) return fail(IKF_EINVAL, "ikf_flow_inverse_gather: flow is NULL");
+  if (flow->n_ranks < 1) return fail(IKF_EINVAL, "ikf_flow_inverse_gather: call ikf_flow_set_peers first");
+  if (batch < 1) return fail(IKF_EINVAL, "ikf_flow_inverse_gather: every rank needs at least one row (got %d)", batch);
+  if (gather_ld < out_cols || row0 < 0) return fail(IKF_EINVAL, "ikf_flow_inverse_gather: bad gathered layout (ld %d, row0 %d)", gather_ld, row0);
+  GatherArgs g{gather_offset, gather_ld, row0};
+  float* own = flow->peer_out[flow->rank] + gather_offset + (size_t)row0 * gather_ld;
+  return flow_launch(flow, latent, latent_ld, cond, cond_ld, cond_rows, cond_cols, own, gather_ld, out_cols, batch,
+                     flow->desc.nb_nodes - 1, 0, 1, clamp, stream, "ikf_flow_inverse_gather", 0, nullptr, &g);
 }
 
 int ikf_flow_set_forward_tables(IkfFlow* flow, const float* m, float log_det_m) {

@@ -36,6 +36,7 @@ constexpr int kSmallFloats = kSmallLastB + kPad;  // 2320
 constexpr int kSmallBytes = kSmallFloats * 4;     // 9280, multiple of 16
 static_assert(kSmallBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
 
+constexpr int kMaxPeers = 8;   // GPUs of one node
 constexpr float kLeakySlope = 0.01f;  // nn.LeakyReLU() default, ikflow/model.py:74-83
 
 struct FlowParams {
@@ -75,6 +76,16 @@ struct FlowParams {
   // chunk and multicasts it to all of them (one L2 read instead of `cluster`).  CTA -> (team slot, feature tile t):
   //   c = blockIdx.x / cluster, r = blockIdx.x % cluster (= %cluster_ctarank), t = c % NT, slot = (c / NT) * cluster + r
   int cluster;
+  // Fused gather of the batch-sharded solve (tcgen05 engine; n_peers = 0: off).  The ranks of one node each solve a
+  // contiguous block of rows; instead of a collective after the kernel, the final epilogue stores its rows straight into
+  // the gathered buffer of EVERY rank (peer-mapped pointers: NVLink stores), and the last CTA to finish raises this
+  // rank's flag on every rank.
+  float* peer_out[kMaxPeers];       // [rank r] base of r's gathered buffer [rows_total][peer_ld] (own rank included)
+  uint32_t* peer_flag[kMaxPeers];   // [rank r] r's flag array [n_peers]: entry `peer_rank` = sequence number of my last shard
+  int n_peers, peer_rank, peer_row0, peer_ld;
+  uint32_t peer_seq;
+  uint32_t* peer_counter;           // device counter of finished writer CTAs (monotonic)
+  uint32_t peer_count_target;       // its value when the last writer CTA of this launch has counted itself
   int forward;         // 1: x -> z with log-det (blocks block_last..block_first ascending), tcgen05 engine only
   float logdet_m;      // FixedLinearTransform.logDetM
   float* logdet_out;   // [batch] (forward pass)
@@ -169,6 +180,14 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 __device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
   uint32_t v;

@@ -115,33 +115,60 @@ struct Cfg {
   static constexpr int kEpiRows = RT / kGroups;
   static constexpr int kEpiWarps = 4 * kGroups;
   static constexpr int kEpiThreads = 32 * kEpiWarps;
-  static constexpr int kStages = RT == 32 ? 4 : (RT == 64 ? 3 : 2);
+  static constexpr int kStages = RT == 32 ? 4 : (RT == 64 ? 3 : 2);  // JIT kernel: stages of the unified ring
+  // Kernels without the just-in-time first layer keep the two operands in SEPARATE rings: a stage of the unified ring
+  // is 64 KB at 128 rows, two of them fill the shared memory, and with ONE chunk in flight every chunk costs a full L2
+  // round trip (1800 cycles against 770 of tensor-core work).  Weights (32 KB per chunk, the same for every row-group
+  // size) and activations (256 B per row and chunk) each get the depth the shared memory allows, each has its own
+  // loader warp and its own full / empty barriers; the last layer's fp32 scratch (`vt`) lives in the activation ring,
+  // which is idle while it is needed (nothing is exchanged between the end of a subnet's second hidden layer and the
+  // publication of the next subnet's first layer).
+  static constexpr bool kSplit = !JIT;
+  static constexpr int kWStages = RT == 128 ? 3 : 4;
+  static constexpr int kAStages = RT == 128 ? 2 : (RT == 64 ? 3 : 4);
   // loader warp w owns the ring stages s with s % kLoaders == w: its waits on a stage's barriers are then strictly in
   // order (a waiter may lag an mbarrier by at most one phase)
   // JIT: two loader warps (each owns two stages), so that the CTA stays at 11 warps: with 13 the register file grants
   // only 128 registers per thread and the epilogue spills
-  static constexpr int kLoaders = JIT ? 2 : (kStages < kLoaderWarps ? kStages : kLoaderWarps);
-  static_assert(kStages % kLoaders == 0, "every stage needs exactly one owner");
+  // split rings: one weight loader warp, one activation loader warp (the lanes of a warp take the stages in turn: copies
+  // of different threads are processed side by side)
+  static constexpr int kLoaders = 2;
+  static_assert(!JIT || kStages % kLoaders == 0, "every stage needs exactly one owner");
   static constexpr int kLoaderWarp0 = kEpiWarps;  // first loader warp
-  static constexpr int kMmaWarp = kEpiWarps + kLoaders;
+  // MMA-issuing warps: warp m takes the k-chunks i = m (mod kMmaWarps) of every hidden layer and accumulates them in its
+  // own TMEM tile, the epilogue adds the tiles in a fixed order.  Measured with 2 (round 2, same box): NO gain at any
+  // row-group size -- the hidden layers are not paced by the issuing thread but by the shared memory, which feeds the
+  // tensor core (44 KB of operand reads per chunk at 32 rows) while the bulk copies write the next chunks into it (40 KB):
+  // 84 KB / ~140 B/clk = 600 cycles per chunk against 430 of MMAs alone; 144 KB -> 1030 cycles at 128 rows (measured 840 /
+  // 1280).  One warp it stays.
+  static constexpr int kMmaWarps = 1;
+  static constexpr int kMmaWarp = kEpiWarps + kLoaders;  // first of them
   // registers are granted per 4 warps: up to 12 warps leave 170 registers per thread, 13+ would leave 128
   // JIT: four more SIMT warps that only help with the just-in-time first layer (8 warps x 8 features per chunk)
   static constexpr int kHelpers = JIT ? 4 : 0;
-  static constexpr int kHelperWarp0 = kMmaWarp + 1;
+  static constexpr int kHelperWarp0 = kMmaWarp + kMmaWarps;
   static constexpr int kGenWarps = kEpiWarps + kHelpers;
   static constexpr int kGenThreads = 32 * kGenWarps;
-  static constexpr int kThreads = (kMmaWarp + 1 + kHelpers) * 32;
+  static constexpr int kThreads = (kMmaWarp + kMmaWarps + kHelpers) * 32;
   static constexpr int kVtBytes = 32 * kFTU * 4;         // fp32 [32 rows][128 features] of one group: last-layer operand
-  static constexpr int kTmemCols = 2 * RT <= 32 ? 32 : (2 * RT <= 64 ? 64 : (2 * RT <= 128 ? 128 : 256));  // D[:, 0:2RT]
+  static constexpr int kAccCols = 2 * RT;  // one accumulator tile: D[:, 0:2RT] (N-stacked products)
+  static constexpr int kTmemCols = kMmaWarps * kAccCols <= 32 ? 32 : (kMmaWarps * kAccCols <= 64 ? 64 : (kMmaWarps * kAccCols <= 128 ? 128 : (kMmaWarps * kAccCols <= 256 ? 256 : 512)));
+  static_assert(kMmaWarps * kAccCols <= 512, "TMEM has 512 columns");
   static_assert(kStage % 1024 == 0, "stages must keep the 1024-byte alignment of the swizzle atoms");
+  static_assert(kAChunk % 1024 == 0, "stages must keep the 1024-byte alignment of the swizzle atoms");
+  static_assert(JIT || kGroups * kVtBytes <= kAStages * kAChunk, "the last layer's scratch must fit the activation ring");
 };
 
 template <int RT, bool JIT = false>
 struct __align__(1024) Smem {
   using C = Cfg<RT, JIT>;
-  uint8_t ring[C::kStages][C::kStage];  // [weights head|tail][activations head|tail]
-  // per epilogue group: fp32 activations [32 rows][128 features] for the last layer (float4 slots swizzled)
-  uint8_t vt[C::kGroups][C::kVtBytes];
+  // JIT kernel: unified ring [weights head|tail][activations head|tail][first-layer weights]; the others: split rings
+  uint8_t ring[JIT ? C::kStages : 1][JIT ? C::kStage : 1024];
+  uint8_t wring[JIT ? 1 : C::kWStages][JIT ? 1024 : kWChunkU];   // [head | tail] x [128 features][64 k]
+  uint8_t aring[JIT ? 1 : C::kAStages][JIT ? 1024 : C::kAChunk];  // [head | tail] x [RT rows][64 k]
+  // per epilogue group: fp32 activations [32 rows][128 features] for the last layer (float4 slots swizzled); the kernels
+  // with split rings keep it in `aring` instead
+  uint8_t vt[JIT ? C::kGroups : 1][JIT ? C::kVtBytes : 1024];
   float small[2][C::kSmFloats];
   float u[RT][kPad];  // flow state
   float cnd[RT][8];
@@ -149,6 +176,7 @@ struct __align__(1024) Smem {
   // input of the current subnet [state half | condition | 0] at its start, output of its last layer at its end
   float a[RT][kPad];
   uint64_t full[C::kStages], empty[C::kStages];
+  uint64_t wfull[C::kWStages], wempty[C::kWStages], afull[C::kAStages], aempty[C::kAStages];  // split rings
   uint64_t w1full[C::kStages];   // JIT: the first-layer weights of the stage's chunk have landed
   uint64_t w1empty[C::kStages];  // JIT: ... and have been used (the stage's weight/activation areas may still be busy)
   uint64_t small_full[2], small_empty[2];
@@ -432,11 +460,19 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
       mbar_init(&sm.w1full[s], 1);
       mbar_init(&sm.w1empty[s], 1);
     }
+    for (int s = 0; s < C::kWStages; ++s) {
+      mbar_init(&sm.wfull[s], 1);
+      mbar_init(&sm.wempty[s], IKF_CS);
+    }
+    for (int s = 0; s < C::kAStages; ++s) {
+      mbar_init(&sm.afull[s], 1);
+      mbar_init(&sm.aempty[s], 1);
+    }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&sm.small_full[b], 1);
       mbar_init(&sm.small_empty[b], C::kEpiWarps);
     }
-    mbar_init(&sm.dfull, 1);
+    mbar_init(&sm.dfull, C::kMmaWarps);
     mbar_init(&sm.dempty, C::kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
@@ -561,143 +597,244 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
       for (int k = lane; k < KCH; k += 32)
         if (k % p.slots == slot) bulk_prefetch_l2(wnext + (size_t)k * kWChunkU, kWChunkU);
     };
-    if (lw == 0) prefetch_small(0);
-    bool gave_up = false;
-    for (int g = 0; g < total_steps; ++g) {
-      const int n = step_subnet(g);
-      for (int l = 0; l < p.n_big; ++l) {
-        const int buf = xchg & 1;
-        const uint32_t expected = p.epoch + 1 + act_w[buf];
-        const uint8_t* wbase =
-            reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n * p.n_big + l) * NT + t) * KCH * kWChunkU;
-        const uint8_t* abase = act_slot + (size_t)buf * NT * kAStrideU;
-        const uint32_t* my_flag = aflag + buf * NT + (lane < NT ? lane : 0);
-        bool prefetched = lw != C::kLoaders - 1;  // the last loader warp pulls weights into L2, see prefetch_layer
-        // JIT: the activations of the first hidden layer are written into the stage by this CTA's own SIMT warps;
-        // the loader brings the first-layer weights of the chunk's 64 features instead, and nothing is exchanged
-        const bool jit_layer = JIT && l == 0;
-        const uint8_t* w1base = reinterpret_cast<const uint8_t*>(p.first_jit) + (size_t)n * KCH * kJitChunkBytes;
-        uint32_t ready = (gave_up || jit_layer) ? 0xffffffffu : 0u;  // bit c: producer c has published (warp-uniform)
-        for (int i = (lw + C::kLoaders - (int)(ring_pos % C::kLoaders)) % C::kLoaders; i < KCH; i += C::kLoaders) {
-          const uint32_t pos = ring_pos + i;
-          const int st = pos % kStages;
-          const uint32_t use = pos / kStages;
-          // everything that does not depend on the stage being free is computed before the wait
-          const int kc = (2 * t + i) % KCH;
-          const int c = kc >> 1;
-          const void* wsrc = wbase + (size_t)kc * kWChunkU;
-          const void* asrc = abase + (size_t)c * kAStrideU + (size_t)(kc & 1) * C::kAChunk;
-          // lane 0 copies the weights, lane 1 the activations: copies of one thread are processed one after the other,
-          // copies of different threads side by side (scripts/ubench/ingest2.cu)
-          const void* my_src = lane == 0 ? wsrc : (jit_layer ? (const void*)(w1base + (size_t)kc * kJitChunkBytes) : asrc);
-          uint8_t* my_dst = sm.ring[st] + (lane == 0 ? 0 : (jit_layer ? C::kW1Off : kWChunkU));
-          const uint32_t my_bytes = lane == 0 ? (uint32_t)kWChunkU : (jit_layer ? (uint32_t)kJitChunkBytes : (uint32_t)C::kAChunk);
-          uint64_t* my_bar = (jit_layer && lane == 1) ? &sm.w1full[st] : &sm.full[st];
-          if (jit_layer) {
-            // the first-layer weights have their own, earlier, hand-over: their area of the stage is free as soon as the
-            // SIMT warps have used it, a chunk time or more before the tensor core lets go of the rest of the stage
-            const uint32_t w1use = (uint32_t)g * (uint32_t)(KCH / kStages) + (uint32_t)(i / kStages);
-            if (w1use > 0) mbar_wait_relaxed(&sm.w1empty[st], (w1use - 1) & 1);
-            if (lane == 1) {
-              mbar_arrive_expect_tx(&sm.w1full[st], kJitChunkBytes);
-              bulk_g2s(my_dst, my_src, my_bytes, my_bar);
+    if constexpr (!JIT) {
+      // ===== split rings (see Cfg::kSplit): loader warp 0 streams the weights, loader warp 1 the exchanged activations;
+      // chunk number pos (counted over the whole launch) goes to stage pos % depth of its ring, issued by lane = stage =====
+      if (lw == 0) {
+        prefetch_small(0);
+        uint32_t pos = 0;
+        for (int g = 0; g < total_steps; ++g) {
+          const int n = step_subnet(g);
+          for (int l = 0; l < p.n_big; ++l) {
+            const uint8_t* wbase =
+                reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n * p.n_big + l) * NT + t) * KCH * kWChunkU;
+            for (int i = 0; i < KCH; ++i, ++pos) {
+              const int st = pos % C::kWStages;
+              const uint32_t use = pos / C::kWStages;
+              const int kc = (2 * t + i) % KCH;
+              if (use > 0) mbar_wait_relaxed(&sm.wempty[st], (use - 1) & 1);  // clusters: free in EVERY CTA of the cluster
+              if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 32 + i);
+              if (lane == st) {
+                mbar_arrive_expect_tx(&sm.wfull[st], kWChunkU);
+                if (p.cluster > 1) {  // this CTA's share of the chunk, delivered to all CTAs of the cluster
+                  const uint32_t share = (uint32_t)kWChunkU / (uint32_t)p.cluster;
+                  const uint32_t off = (blockIdx.x % (uint32_t)p.cluster) * share;
+                  bulk_g2s_multicast(sm.wring[st] + off, wbase + (size_t)kc * kWChunkU + off, share, &sm.wfull[st], (uint16_t)((1u << p.cluster) - 1u));
+                } else {
+                  bulk_g2s(sm.wring[st], wbase + (size_t)kc * kWChunkU, kWChunkU, &sm.wfull[st]);
+                }
+                if (i == 0) trace_ev(p, g * 4 + l, 0);
+              }
+              __syncwarp();
+              if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 80 + i);
+              if (i == 0) {  // after the layer's first copy is on its way: next layers into L2
+                const int q = g * p.n_big + l;
+                const int dist = (p.debug & 32) ? 0 : (p.debug & 64) ? 1 : (p.debug & 128) ? 3 : (p.debug & 256) ? 4 : 2;
+                if (q == 0) for (int d = 1; d < dist; ++d) prefetch_layer(d);
+                if (dist > 0) prefetch_layer(q + dist);
+              }
             }
-            __syncwarp();
+            if (l == 0) prefetch_small(g + 1);
           }
-          if (use > 0) mbar_wait_relaxed(&sm.empty[st], (use - 1) & 1);
-          if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 32 + i);
-          // JIT kernel: the first two chunks of an exchanged layer (i = 0, 1 <-> kc = 2t, 2t+1) are this CTA's own output;
-          // its epilogue warps write them into the stage themselves (and arrive on the full barrier), so that the tensor
-          // core starts on them while the publish / fence / flag / poll round trip of the exchange is still under way
-          const bool own_chunk = JIT && !jit_layer && i < 2;
-          const bool skip_a = jit_layer || own_chunk;  // no activation copy by the loader
-          // one look at the flags: if the producer is already done, weights and activations go out together
-          if (!skip_a && !((ready >> c) & 1u)) {
-            bool ok = false;
-            if (lane < NT && !((ready >> lane) & 1u)) ok = (int32_t)(ld_relaxed(my_flag) - expected) >= 0;
-            ready |= __ballot_sync(0xffffffffu, ok);
-          }
-          const bool a_now = !skip_a && ((ready >> c) & 1u);
-          if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 64 + i);
-          // No ordering is needed between lane 0's expect_tx and lane 1's copy: the phase cannot complete before the
-          // (single) pending arrival, which is the expect_tx itself, whatever the transient sign of the tx-count.
-          if (JIT) {
-            // the full barrier of a stage takes two arrivals per phase: the weights' expect_tx, and the SIMT warps' "the
-            // activations are written" in a JIT layer (a second plain arrival of the loader in the other layers)
-            if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], kWChunkU + (skip_a ? 0 : C::kAChunk));
-            if (lane == 2 && !skip_a) mbar_arrive(&sm.full[st]);
-          } else {
-            if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], (p.debug & 1 ? 0 : C::kAChunk) + (p.debug & 2 ? 0 : kWChunkU));
-          }
-          if (p.cluster > 1 && lane == 0) {
-            // this CTA's share of the weight chunk, delivered to every CTA of the cluster (all of them wait for the same
-            // chunk in the same ring stage; the `empty` barrier above has told us that the stage is free in all of them)
-            const uint32_t share = (uint32_t)kWChunkU / (uint32_t)p.cluster;
-            const uint32_t off = (blockIdx.x % (uint32_t)p.cluster) * share;
-            bulk_g2s_multicast(my_dst + off, (const uint8_t*)my_src + off, share, my_bar, (uint16_t)((1u << p.cluster) - 1u));
-          } else if (lane < (a_now ? 2 : 1) && !((p.debug >> (1 - lane)) & 1)) {
-            bulk_g2s(my_dst, my_src, my_bytes, my_bar);
-          }
-          __syncwarp();
-          if (!prefetched) {  // after this warp's first copies of the layer are on their way
-            prefetched = true;
-            const int q = g * p.n_big + l;
-            const int dist = (p.debug & 32) ? 0 : (p.debug & 64) ? 1 : (p.debug & 128) ? 3 : (p.debug & 256) ? 4 : 2;
-            if (q == 0) for (int d = 1; d < dist; ++d) prefetch_layer(d);
-            if (dist > 0) prefetch_layer(q + dist);
-          }
-          if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 80 + i);
-          if (lane == 0 && i == 0) trace_ev(p, g * 4 + l, 0);
-          if (!a_now && !skip_a) {
-            uint32_t spins = 0;
-            long long t0 = 0;
-            while (!((ready >> c) & 1u)) {
-              bool ok = false;
-              if (lane < NT && !((ready >> lane) & 1u)) ok = (int32_t)(ld_relaxed(my_flag) - expected) >= 0;
-              ready |= __ballot_sync(0xffffffffu, ok);
-              if ((ready >> c) & 1u) break;
-              ++spins;
-              if (spins == 64) t0 = clock64();
-              if (spins > 64) {
-                __nanosleep(20);
-                if ((spins & 255u) == 0) {
-                  int bail = 0;
-                  if (lane == 0) {
-                    if (ld_relaxed(p.status + 1) == launch_id) bail = 1;
-                    else if (clock64() - t0 > 2500000000LL) {
-                      report_timeout(p.status, p.status_host, launch_id);
-                      bail = 1;
+          if (p.n_big == 0) prefetch_small(g + 1);
+        }
+      } else {
+        uint32_t pos = 0;
+        bool gave_up = false;
+        for (int g = 0; g < total_steps; ++g) {
+          for (int l = 0; l < p.n_big; ++l) {
+            const int buf = xchg & 1;
+            const uint32_t expected = p.epoch + 1 + act_w[buf];
+            const uint8_t* abase = act_slot + (size_t)buf * NT * kAStrideU;
+            const uint32_t* my_flag = aflag + buf * NT + (lane < NT ? lane : 0);
+            uint32_t ready = gave_up ? 0xffffffffu : 0u;  // bit c: producer c has published (warp-uniform)
+            for (int i = 0; i < KCH; ++i, ++pos) {
+              const int st = pos % C::kAStages;
+              const uint32_t use = pos / C::kAStages;
+              const int kc = (2 * t + i) % KCH;
+              const int c = kc >> 1;
+              if (use > 0) mbar_wait_relaxed(&sm.aempty[st], (use - 1) & 1);
+              if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 64 + i);
+              uint32_t spins = 0;
+              long long t0 = 0;
+              while (!((ready >> c) & 1u)) {
+                bool ok = false;
+                if (lane < NT && !((ready >> lane) & 1u)) ok = (int32_t)(ld_relaxed(my_flag) - expected) >= 0;
+                ready |= __ballot_sync(0xffffffffu, ok);
+                if ((ready >> c) & 1u) break;
+                ++spins;
+                if (spins == 64) t0 = clock64();
+                if (spins > 64) {
+                  __nanosleep(20);
+                  if ((spins & 255u) == 0) {
+                    int bail = 0;
+                    if (lane == 0) {
+                      if (ld_relaxed(p.status + 1) == launch_id) bail = 1;
+                      else if (clock64() - t0 > 2500000000LL) {
+                        report_timeout(p.status, p.status_host, launch_id);
+                        bail = 1;
+                      }
                     }
-                  }
-                  if (__shfl_sync(0xffffffffu, bail, 0)) {
-                    gave_up = true;
-                    ready = 0xffffffffu;
+                    if (__shfl_sync(0xffffffffu, bail, 0)) {
+                      gave_up = true;
+                      ready = 0xffffffffu;
+                    }
                   }
                 }
               }
+              if (lane == st) {
+                mbar_arrive_expect_tx(&sm.afull[st], C::kAChunk);
+                bulk_g2s(sm.aring[st], abase + (size_t)c * kAStrideU + (size_t)(kc & 1) * C::kAChunk, C::kAChunk, &sm.afull[st]);
+                if (i == 0) trace_ev(p, g * 4 + l, 1);
+                if (i == KCH - 1) trace_ev(p, g * 4 + l, 2);
+              }
+              __syncwarp();
+              if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 48 + i);
             }
-            if (lane == 0 && i == 0) trace_ev(p, g * 4 + l, 3);
-            // lane 1, not lane 0: lane 0's weight copy may still be in flight, and a thread's copies are processed in order
-            if (lane == 1 && !(p.debug & 1)) bulk_g2s(my_dst, my_src, my_bytes, &sm.full[st]);
-            __syncwarp();
+            ++act_w[buf];
+            ++xchg;
           }
-          if (lane == 0) {
-            if (i == 0) trace_ev(p, g * 4 + l, 1);
-            if (i == KCH - 1) trace_ev(p, g * 4 + l, 2);
-            if (p.trace != nullptr && i < 16) trace_clk(p, g * 4 + l, 48 + i);
-          }
-        }
-        if (lw == 0 && l == 0) prefetch_small(g + 1);
-        ring_pos += KCH;
-        if (!jit_layer) {  // a JIT layer is not an exchange
-          ++act_w[buf];
-          ++xchg;
         }
       }
-      if (lw == 0 && p.n_big == 0) prefetch_small(g + 1);
+    } else {
+      if (lw == 0) prefetch_small(0);
+      bool gave_up = false;
+      for (int g = 0; g < total_steps; ++g) {
+        const int n = step_subnet(g);
+        for (int l = 0; l < p.n_big; ++l) {
+          const int buf = xchg & 1;
+          const uint32_t expected = p.epoch + 1 + act_w[buf];
+          const uint8_t* wbase =
+              reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n * p.n_big + l) * NT + t) * KCH * kWChunkU;
+          const uint8_t* abase = act_slot + (size_t)buf * NT * kAStrideU;
+          const uint32_t* my_flag = aflag + buf * NT + (lane < NT ? lane : 0);
+          bool prefetched = lw != C::kLoaders - 1;  // the last loader warp pulls weights into L2, see prefetch_layer
+          // JIT: the activations of the first hidden layer are written into the stage by this CTA's own SIMT warps;
+          // the loader brings the first-layer weights of the chunk's 64 features instead, and nothing is exchanged
+          const bool jit_layer = JIT && l == 0;
+          const uint8_t* w1base = reinterpret_cast<const uint8_t*>(p.first_jit) + (size_t)n * KCH * kJitChunkBytes;
+          uint32_t ready = (gave_up || jit_layer) ? 0xffffffffu : 0u;  // bit c: producer c has published (warp-uniform)
+          for (int i = (lw + C::kLoaders - (int)(ring_pos % C::kLoaders)) % C::kLoaders; i < KCH; i += C::kLoaders) {
+            const uint32_t pos = ring_pos + i;
+            const int st = pos % kStages;
+            const uint32_t use = pos / kStages;
+            // everything that does not depend on the stage being free is computed before the wait
+            const int kc = (2 * t + i) % KCH;
+            const int c = kc >> 1;
+            const void* wsrc = wbase + (size_t)kc * kWChunkU;
+            const void* asrc = abase + (size_t)c * kAStrideU + (size_t)(kc & 1) * C::kAChunk;
+            // lane 0 copies the weights, lane 1 the activations: copies of one thread are processed one after the other,
+            // copies of different threads side by side (scripts/ubench/ingest2.cu)
+            const void* my_src = lane == 0 ? wsrc : (jit_layer ? (const void*)(w1base + (size_t)kc * kJitChunkBytes) : asrc);
+            uint8_t* my_dst = sm.ring[st] + (lane == 0 ? 0 : (jit_layer ? C::kW1Off : kWChunkU));
+            const uint32_t my_bytes = lane == 0 ? (uint32_t)kWChunkU : (jit_layer ? (uint32_t)kJitChunkBytes : (uint32_t)C::kAChunk);
+            uint64_t* my_bar = (jit_layer && lane == 1) ? &sm.w1full[st] : &sm.full[st];
+            if (jit_layer) {
+              // the first-layer weights have their own, earlier, hand-over: their area of the stage is free as soon as the
+              // SIMT warps have used it, a chunk time or more before the tensor core lets go of the rest of the stage
+              const uint32_t w1use = (uint32_t)g * (uint32_t)(KCH / kStages) + (uint32_t)(i / kStages);
+              if (w1use > 0) mbar_wait_relaxed(&sm.w1empty[st], (w1use - 1) & 1);
+              if (lane == 1) {
+                mbar_arrive_expect_tx(&sm.w1full[st], kJitChunkBytes);
+                bulk_g2s(my_dst, my_src, my_bytes, my_bar);
+              }
+              __syncwarp();
+            }
+            if (use > 0) mbar_wait_relaxed(&sm.empty[st], (use - 1) & 1);
+            if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 32 + i);
+            // JIT kernel: the first two chunks of an exchanged layer (i = 0, 1 <-> kc = 2t, 2t+1) are this CTA's own output;
+            // its epilogue warps write them into the stage themselves (and arrive on the full barrier), so that the tensor
+            // core starts on them while the publish / fence / flag / poll round trip of the exchange is still under way
+            const bool own_chunk = JIT && !jit_layer && i < 2;
+            const bool skip_a = jit_layer || own_chunk;  // no activation copy by the loader
+            // one look at the flags: if the producer is already done, weights and activations go out together
+            if (!skip_a && !((ready >> c) & 1u)) {
+              bool ok = false;
+              if (lane < NT && !((ready >> lane) & 1u)) ok = (int32_t)(ld_relaxed(my_flag) - expected) >= 0;
+              ready |= __ballot_sync(0xffffffffu, ok);
+            }
+            const bool a_now = !skip_a && ((ready >> c) & 1u);
+            if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 64 + i);
+            // No ordering is needed between lane 0's expect_tx and lane 1's copy: the phase cannot complete before the
+            // (single) pending arrival, which is the expect_tx itself, whatever the transient sign of the tx-count.
+            if (JIT) {
+              // the full barrier of a stage takes two arrivals per phase: the weights' expect_tx, and the SIMT warps' "the
+              // activations are written" in a JIT layer (a second plain arrival of the loader in the other layers)
+              if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], kWChunkU + (skip_a ? 0 : C::kAChunk));
+              if (lane == 2 && !skip_a) mbar_arrive(&sm.full[st]);
+            } else {
+              if (lane == 0) mbar_arrive_expect_tx(&sm.full[st], (p.debug & 1 ? 0 : C::kAChunk) + (p.debug & 2 ? 0 : kWChunkU));
+            }
+            if (p.cluster > 1 && lane == 0) {
+              // this CTA's share of the weight chunk, delivered to every CTA of the cluster (all of them wait for the same
+              // chunk in the same ring stage; the `empty` barrier above has told us that the stage is free in all of them)
+              const uint32_t share = (uint32_t)kWChunkU / (uint32_t)p.cluster;
+              const uint32_t off = (blockIdx.x % (uint32_t)p.cluster) * share;
+              bulk_g2s_multicast(my_dst + off, (const uint8_t*)my_src + off, share, my_bar, (uint16_t)((1u << p.cluster) - 1u));
+            } else if (lane < (a_now ? 2 : 1) && !((p.debug >> (1 - lane)) & 1)) {
+              bulk_g2s(my_dst, my_src, my_bytes, my_bar);
+            }
+            __syncwarp();
+            if (!prefetched) {  // after this warp's first copies of the layer are on their way
+              prefetched = true;
+              const int q = g * p.n_big + l;
+              const int dist = (p.debug & 32) ? 0 : (p.debug & 64) ? 1 : (p.debug & 128) ? 3 : (p.debug & 256) ? 4 : 2;
+              if (q == 0) for (int d = 1; d < dist; ++d) prefetch_layer(d);
+              if (dist > 0) prefetch_layer(q + dist);
+            }
+            if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 80 + i);
+            if (lane == 0 && i == 0) trace_ev(p, g * 4 + l, 0);
+            if (!a_now && !skip_a) {
+              uint32_t spins = 0;
+              long long t0 = 0;
+              while (!((ready >> c) & 1u)) {
+                bool ok = false;
+                if (lane < NT && !((ready >> lane) & 1u)) ok = (int32_t)(ld_relaxed(my_flag) - expected) >= 0;
+                ready |= __ballot_sync(0xffffffffu, ok);
+                if ((ready >> c) & 1u) break;
+                ++spins;
+                if (spins == 64) t0 = clock64();
+                if (spins > 64) {
+                  __nanosleep(20);
+                  if ((spins & 255u) == 0) {
+                    int bail = 0;
+                    if (lane == 0) {
+                      if (ld_relaxed(p.status + 1) == launch_id) bail = 1;
+                      else if (clock64() - t0 > 2500000000LL) {
+                        report_timeout(p.status, p.status_host, launch_id);
+                        bail = 1;
+                      }
+                    }
+                    if (__shfl_sync(0xffffffffu, bail, 0)) {
+                      gave_up = true;
+                      ready = 0xffffffffu;
+                    }
+                  }
+                }
+              }
+              if (lane == 0 && i == 0) trace_ev(p, g * 4 + l, 3);
+              // lane 1, not lane 0: lane 0's weight copy may still be in flight, and a thread's copies are processed in order
+              if (lane == 1 && !(p.debug & 1)) bulk_g2s(my_dst, my_src, my_bytes, &sm.full[st]);
+              __syncwarp();
+            }
+            if (lane == 0) {
+              if (i == 0) trace_ev(p, g * 4 + l, 1);
+              if (i == KCH - 1) trace_ev(p, g * 4 + l, 2);
+              if (p.trace != nullptr && i < 16) trace_clk(p, g * 4 + l, 48 + i);
+            }
+          }
+          if (lw == 0 && l == 0) prefetch_small(g + 1);
+          ring_pos += KCH;
+          if (!jit_layer) {  // a JIT layer is not an exchange
+            ++act_w[buf];
+            ++xchg;
+          }
+        }
+        if (lw == 0 && p.n_big == 0) prefetch_small(g + 1);
+      }
     }
-  } else if (warp == C::kMmaWarp) {
-    // ===== MMA issuer: the whole warp runs the loop (warp-uniform control flow), one elected lane drives the tensor
+  } else if (warp >= C::kMmaWarp && warp < C::kMmaWarp + C::kMmaWarps) {
+    // ===== MMA issuers (see Cfg::kMmaWarps): the whole warp runs the loop (warp-uniform control flow), one elected lane drives the tensor
     // core.  With `if (lane == 0)` around the loop ptxas wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY
     // loop ("once per active thread"); behind elect.sync the UTCHMMAs are emitted back to back: 840 -> 560 cycles per
     // k-chunk for the issuing thread (scripts/ubench/umma_loop.cu), which is what paces the hidden layers. =====
@@ -709,52 +846,62 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
       const bool x3 = p.precision != IKF_PRECISION_BF16X1;
       const uint64_t d_wh0 = make_desc(smem_u32(sm.ring[0])), d_wl0 = make_desc(smem_u32(sm.ring[0]) + kWPlaneU);
       const uint64_t d_a0 = make_desc(smem_u32(sm.ring[0]) + kWChunkU);
-      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const int mw = warp - C::kMmaWarp;  // this warp's chunks: i = mw (mod kMmaWarps), its accumulator tile: mw
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0) + (uint32_t)(mw * C::kAccCols);
       const uint32_t tmem_u2 = tmem_u + (F16 ? RT : 0);  // fp16x3: the scaled correction terms have their own accumulator
-      const bool static_ring = (KCH % kStages) == 0;  // every layer then starts at ring stage 0
       for (int g = 0; g < total_steps; ++g) {
         for (int l = 0; l < p.n_big; ++l) {
-          if (layers > 0) mbar_wait(&sm.dempty, (layers - 1) & 1);  // the epilogue has drained the accumulator
+          if (layers > 0) mbar_wait(&sm.dempty, (layers - 1) & 1);  // the epilogue has drained the accumulators
           tc_fence_after();
-          if (static_ring) {
-            // stage index = i % kStages is a compile-time constant inside the unrolled group: the 3 descriptors of every
-            // stage stay in uniform registers (428 instead of 459 cycles of issue per chunk, scripts/ubench/umma_loop.cu)
+          if constexpr (C::kSplit) {
+            // split rings: chunk number ring_pos + i sits in weight stage (ring_pos + i) % kWStages and activation stage
+            // (ring_pos + i) % kAStages
+            const uint64_t d_w0 = make_desc(smem_u32(&sm.wring[0][0])), d_as0 = make_desc(smem_u32(&sm.aring[0][0]));
+            for (int i = mw; i < KCH; i += C::kMmaWarps) {
+              const uint32_t pos = ring_pos + (uint32_t)i;
+              const int sw = pos % C::kWStages, sa = pos % C::kAStages;
+              mbar_wait(&sm.wfull[sw], (pos / C::kWStages) & 1);
+              mbar_wait(&sm.afull[sa], (pos / C::kAStages) & 1);
+              tc_fence_after();
+              if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 16 + i);
+              const uint64_t dwh = d_w0 + (uint64_t)(sw * (kWChunkU >> 4)), da = d_as0 + (uint64_t)(sa * (C::kAChunk >> 4));
+              if (elect_one()) {
+                if (x3)
+                  mma_chunk_x3(tmem_u, tmem_u2, idesc2, idesc, dwh, dwh + (uint64_t)(kWPlaneU >> 4), da, i >= C::kMmaWarps);
+                else
+                  mma_chunk_x1(tmem_u, idesc, dwh, da, i >= C::kMmaWarps);
+                // both stages are free once these MMAs have read them (clusters: the weight stage is refilled by every CTA)
+                if (p.cluster > 1) mma_commit_multicast(&sm.wempty[sw], (uint16_t)((1u << p.cluster) - 1u)); else mma_commit(&sm.wempty[sw]);
+                mma_commit(&sm.aempty[sa]);
+              }
+              __syncwarp();
+            }
+            ring_pos += KCH;
+          } else {
+            // unified ring (just-in-time kernel; every layer starts at stage 0): stage index = i % kStages is a compile-time
+            // constant inside the unrolled group, so the 3 descriptors of every stage stay in uniform registers (428 instead
+            // of 459 cycles of issue per chunk, scripts/ubench/umma_loop.cu); warp mw owns the stages s = mw (mod 2)
+            static_assert(C::kSplit || kStages % C::kMmaWarps == 0, "stages are dealt to the MMA warps");
             for (int i0 = 0; i0 < KCH; i0 += kStages) {
               const uint32_t par = (ring_pos / kStages) & 1;
 #pragma unroll
               for (int s = 0; s < kStages; ++s) {
+                if ((s % C::kMmaWarps) != mw) continue;
                 mbar_wait(&sm.full[s], par);
                 tc_fence_after();
                 if (p.trace != nullptr && lane == 0 && i0 + s < 16) trace_clk(p, g * 4 + l, 16 + i0 + s);
                 constexpr uint64_t kStageOff = (uint64_t)(C::kStage >> 4);  // stage offset in the 16-byte address field
                 if (elect_one()) {
                   if (x3)
-                    mma_chunk_x3(tmem_u, tmem_u2, idesc2, idesc, d_wh0 + s * kStageOff, d_wl0 + s * kStageOff, d_a0 + s * kStageOff, (i0 + s) != 0);
+                    mma_chunk_x3(tmem_u, tmem_u2, idesc2, idesc, d_wh0 + s * kStageOff, d_wl0 + s * kStageOff, d_a0 + s * kStageOff, (i0 + s) >= C::kMmaWarps);
                   else
-                    mma_chunk_x1(tmem_u, idesc, d_wh0 + s * kStageOff, d_a0 + s * kStageOff, (i0 + s) != 0);
+                    mma_chunk_x1(tmem_u, idesc, d_wh0 + s * kStageOff, d_a0 + s * kStageOff, (i0 + s) >= C::kMmaWarps);
                   // the stage is free once these MMAs have read it (clusters: tell every CTA that refills it)
                   if (p.cluster > 1) mma_commit_multicast(&sm.empty[s], (uint16_t)((1u << p.cluster) - 1u)); else mma_commit(&sm.empty[s]);
                 }
                 __syncwarp();
               }
               ring_pos += kStages;
-            }
-          } else {
-            for (int i = 0; i < KCH; ++i) {
-              const int s = ring_pos % kStages;
-              mbar_wait(&sm.full[s], (ring_pos / kStages) & 1);
-              tc_fence_after();
-              if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 16 + i);
-              const uint64_t soff = (uint64_t)(s * (C::kStage >> 4));
-              if (elect_one()) {
-                if (x3)
-                  mma_chunk_x3(tmem_u, tmem_u2, idesc2, idesc, d_wh0 + soff, d_wl0 + soff, d_a0 + soff, i != 0);
-                else
-                  mma_chunk_x1(tmem_u, idesc, d_wh0 + soff, d_a0 + soff, i != 0);
-                if (p.cluster > 1) mma_commit_multicast(&sm.empty[s], (uint16_t)((1u << p.cluster) - 1u)); else mma_commit(&sm.empty[s]);
-              }
-              __syncwarp();
-              ++ring_pos;
             }
           }
           if (elect_one()) mma_commit(&sm.dfull);  // accumulator complete
@@ -778,7 +925,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
     uint32_t axchg = 0;          // activation exchanges so far
     uint32_t layers = 0;         // hidden layers drained so far
     const bool x3 = p.precision != IKF_PRECISION_BF16X1;
-    const uint32_t vt_a = smem_u32(sm.vt[h]);
+    const uint32_t vt_a = JIT ? smem_u32(sm.vt[h]) : smem_u32(&sm.aring[0][0]) + h * C::kVtBytes;
     const int j8 = lane & 7;     // publish: row inside an 8-row block after the lane transpose
     const uint32_t xin_a = smem_u32(&sm.a[0][0]);
     const bool tiled_first = !JIT && !(p.debug & 4096);
@@ -926,15 +1073,18 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
               if (tid == 0) trace_ev(p, g * 4 + l - 1, 7);
 #pragma unroll
               for (int c0 = 0; c0 < ER; c0 += 32) {
-                float tmp[32], tmp2[32];
-                tmem_ld32(taddr + row0 + c0, tmp);  // bf16x3: W_head*A_head + W_tail*A_head; fp16x3: W_head*A_head
-                if (x3) {
-                  tmem_ld32(taddr + RT + row0 + c0, tmp2);  // bf16x3: W_head*A_tail; fp16x3: 2^11 (W_head*A_tail + W_tail*A_head)
+                // the tiles of the two MMA warps (even / odd k-chunks), added in a fixed order
 #pragma unroll
-                  for (int r = 0; r < 32; ++r) v[c0 + r] = F16 ? fmaf(tmp2[r], 1.f / kTailScaleF16, tmp[r]) : tmp[r] + tmp2[r];
-                } else {
+                for (int m = 0; m < C::kMmaWarps; ++m) {
+                  float tmp[32], tmp2[32];
+                  tmem_ld32(taddr + m * C::kAccCols + row0 + c0, tmp);  // bf16x3: W_head*A_head + W_tail*A_head; fp16x3: W_head*A_head
+                  if (x3) {
+                    tmem_ld32(taddr + m * C::kAccCols + RT + row0 + c0, tmp2);  // bf16x3: W_head*A_tail; fp16x3: 2^11 (W_head*A_tail + W_tail*A_head)
 #pragma unroll
-                  for (int r = 0; r < 32; ++r) v[c0 + r] = tmp[r];
+                    for (int r = 0; r < 32; ++r) tmp[r] = F16 ? fmaf(tmp2[r], 1.f / kTailScaleF16, tmp[r]) : tmp[r] + tmp2[r];
+                  }
+#pragma unroll
+                  for (int r = 0; r < 32; ++r) v[c0 + r] = m == 0 ? tmp[r] : v[c0 + r] + tmp[r];
                 }
               }
               tc_fence_before();
@@ -1174,6 +1324,8 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
             if (!isfinite(o)) report_nonfinite(p.status, p.status_host);
           }
           p.out[(size_t)row * p.out_ld + j] = o;
+          // fused gather: the same value into the gathered buffer of every rank of the node (NVLink stores)
+          for (int r = 0; r < p.n_peers; ++r) p.peer_out[r][(size_t)(p.peer_row0 + row) * p.peer_ld + j] = o;
         }
         if (p.forward && p.logdet_out != nullptr)
           for (int r = tid; r < RT; r += ET)
@@ -1183,6 +1335,20 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
     }
   }
 
+  if (p.n_peers > 0 && t == 0 && warp < C::kEpiWarps) {
+    // fused gather: this CTA's rows are on their way to every rank.  The last writer CTA of the launch publishes the
+    // shard: fence (system scope, cumulative over the stores the barrier / the counter ordered before it), then this rank's
+    // sequence number into the flag array of every rank.
+    bar_epi<ET>();
+    if (tid == 0) {
+      __threadfence_system();
+      const uint32_t old = atomicAdd(p.peer_counter, 1u);
+      if (old + 1u == p.peer_count_target) {
+        __threadfence_system();
+        for (int r = 0; r < p.n_peers; ++r) st_release_sys(p.peer_flag[r] + p.peer_rank, p.peer_seq);
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (p.cluster > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or arrive on its barriers
@@ -1192,6 +1358,22 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
 }
 
 #undef IKF_CS
+
+// Fused gather, consumer side: returns (in stream order) when every rank's shard of sequence number `seq` has arrived in
+// this rank's gathered buffer.  One warp, lane r polls rank r's flag; bounded like every other wait of the library.
+__global__ void __launch_bounds__(32) wait_peers_kernel(const uint32_t* flags, int n_peers, uint32_t seq, uint32_t* status, uint32_t* status_host) {
+  const int r = threadIdx.x;
+  if (r >= n_peers) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while ((int32_t)(ld_acquire_sys(flags + r) - seq) < 0) {
+    if (++spins > 64) __nanosleep(100);
+    if ((spins & 1023u) == 0 && clock64() - t0 > 6000000000LL) {  // ~3 s: a peer never published
+      report_timeout(status, status_host, seq);
+      return;
+    }
+  }
+}
 
 }  // namespace umma
 }  // namespace ikf

@@ -11,6 +11,8 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
+from .ikflow_solver import draw_latent
+
 
 def shard_bounds(n: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Rows [lo, hi) of rank ``rank``: contiguous blocks, the first ``n % world_size`` ranks get one extra row."""
@@ -77,3 +79,52 @@ def generate_exact_ik_solutions_sharded(solver, target_poses: torch.Tensor, gath
     packed = torch.cat([sol, valid.to(sol.dtype).unsqueeze(1)], dim=1)  # one collective for both
     packed = all_gather_rows(packed, n, group)
     return packed[:, :-1].contiguous(), packed[:, -1] > 0.5
+
+
+class PeerGather:
+    """The gather fused into the flow kernel (the alternative to the collective).
+
+    Every rank allocates the SAME symmetric buffer -- two gathered tensors ``[n_total, ndof]`` (ping-pong) -- plus a flag
+    array, and maps its peers' copies (``torch.distributed._symmetric_memory``: CUDA VMM handles exchanged over the
+    process group, NVLink P2P).  ``generate_ik_solutions`` then is ONE flow launch whose final epilogue stores this rank's
+    joint angles into the gathered tensor of every rank, followed by a one-warp kernel that waits for the other ranks'
+    shards: no NCCL call on the critical path.  All ranks must call it the same number of times (SPMD), each with
+    the rows ``shard_bounds(n_total, rank, world)`` of the batch; the returned tensor is valid until the call after the
+    next one.
+    """
+
+    def __init__(self, solver, n_total: int, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.solver, self.group = solver, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n_total, self.ndof = int(n_total), solver.ndof
+        assert self.n_total >= self.world, "the fused gather needs at least one row per rank (use all_gather_rows otherwise)"
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.words = 2 * self.n_total * self.ndof
+        self.flag_off = (self.words + 31) // 32 * 32  # flags behind the two gathered tensors, 128-byte aligned
+        self.buf = symm_mem.empty(self.flag_off + 32, dtype=torch.float32, device=self.device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, dist.group.WORLD if group is None else group)
+        torch.cuda.synchronize()
+        dist.barrier(group)  # every rank's flags are zero before anybody launches
+        base = [int(x) for x in self.handle.buffer_ptrs]
+        solver.nn_model.set_peers(self.device, self.world, self.rank, base, [b + 4 * self.flag_off for b in base])
+        self.calls = 0
+        self.lo, self.hi = shard_bounds(self.n_total, self.rank, self.world)
+
+    def generate_ik_solutions(self, target_poses_local: torch.Tensor, latent_local: Optional[torch.Tensor] = None,
+                              latent_distribution: str = "gaussian", latent_scale: float = 1.0, clamp_to_joint_limits: bool = True) -> torch.Tensor:
+        """``generate_ik_solutions`` for this rank's rows + the fused gather; returns the gathered ``[n_total, ndof]``."""
+        n = self.hi - self.lo
+        assert target_poses_local.shape == (n, 7), f"expected this rank's {n} poses, got {tuple(target_poses_local.shape)}"
+        assert self.solver._model_weights_loaded, "Model weights have not been loaded. Call load_state_dict(...)"
+        if latent_local is None:
+            latent_local = draw_latent(latent_distribution, latent_scale, (n, self.solver.network_width), target_poses_local.device)
+        half = self.calls & 1
+        self.calls += 1
+        self.solver.nn_model.inverse_gather(latent_local, target_poses_local, self.ndof, clamp_to_joint_limits, half * self.n_total * self.ndof, self.ndof, self.lo)
+        return self.buf[half * self.n_total * self.ndof : (half + 1) * self.n_total * self.ndof].view(self.n_total, self.ndof)
+
+    def close(self):
+        self.solver.nn_model.set_peers(self.device, 0, 0, [], [])

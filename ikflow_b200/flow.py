@@ -173,6 +173,26 @@ class FlowModel:
         _lib.check(code, "ikf_flow_inverse")
         return out
 
+    # ---- fused gather of the batch-sharded solve (see ikflow_b200/distributed.py: PeerGather) -------------------------------
+    def set_peers(self, device: torch.device, n_ranks: int, rank: int, gather_ptrs: Sequence[int], flag_ptrs: Sequence[int]) -> None:
+        """``ikf_flow_set_peers``: peer-mapped base pointers of every rank's gathered buffer and flag array."""
+        bufs = (ctypes.c_void_p * max(n_ranks, 1))(*[ctypes.c_void_p(int(x)) for x in gather_ptrs])
+        flags = (ctypes.c_void_p * max(n_ranks, 1))(*[ctypes.c_void_p(int(x)) for x in flag_ptrs])
+        _lib.check(_lib.lib().ikf_flow_set_peers(self._handle(device), n_ranks, rank, bufs, flags), "ikf_flow_set_peers")
+
+    def inverse_gather(self, latent: torch.Tensor, cond: torch.Tensor, out_cols: int, clamp: bool, gather_offset: int, gather_ld: int, row0: int) -> None:
+        """The reverse pass of this rank's rows with the gather fused into the kernel's epilogue (``ikf_flow_inverse_gather``):
+        rows [row0, row0 + n) of the gathered tensor at ``gather_offset`` floats inside every rank's symmetric buffer."""
+        self._check_inputs(latent, cond, self.ndim_tot, self.dim_cond)
+        batch = latent.shape[0]
+        assert cond.shape[0] >= 1 and batch % cond.shape[0] == 0, f"{batch} rows vs {cond.shape[0]} condition rows"
+        latent, cond = latent.contiguous(), cond.contiguous()
+        code = _lib.lib().ikf_flow_inverse_gather(
+            self._handle(latent.device), latent.data_ptr(), latent.stride(0), cond.data_ptr(), cond.stride(0), cond.shape[0],
+            cond.shape[1], out_cols, batch, int(clamp), gather_offset, gather_ld, row0, torch.cuda.current_stream(latent.device).cuda_stream,
+        )
+        _lib.check(code, "ikf_flow_inverse_gather")
+
     def forward_pass(self, x: torch.Tensor, cond: torch.Tensor):
         """x -> z with its log-determinant, ``nn_model(x, c=cond, rev=False)`` (``ikflow/training/lt_model.py:156``), in one
         launch.  Inference only: no gradients flow through it."""

@@ -132,6 +132,28 @@ int ikf_flow_inverse_blocks(IkfFlow* flow, const float* state_in, int in_ld, con
 int ikf_flow_forward(IkfFlow* flow, const float* x, int x_ld, const float* cond, int cond_ld, int cond_rows, int cond_cols,
                      float* z_out, int out_ld, float* logdet_out, int batch, void* stream);
 
+/* ---- fused gather of the batch-sharded solve (multi-GPU, one process per GPU) -------------------------------------------
+ * The reference has no multi-GPU path; BASELINE's north star shards the batch over up to 8 GPUs and gathers the joint
+ * angles with one NCCL all-gather.  The fused alternative removes the collective from the critical path: the kernel's
+ * final epilogue stores its rows into the gathered buffer of EVERY rank (peer-mapped device pointers, NVLink stores) and
+ * the last CTA raises this rank's flag on every rank; ikf_flow_inverse_gather then queues a one-warp kernel that waits
+ * (stream-ordered) for the flags of all ranks.
+ *
+ * ikf_flow_set_peers: gather_bufs[r] = base of rank r's symmetric allocation as mapped into THIS process (cudaIpc /
+ * torch symmetric memory / cuMem), flag_bufs[r] = rank r's flag array [n_ranks] uint32 (zero-initialised by its owner
+ * before the first call; all ranks must have called set_peers before any rank launches).  n_ranks = 0 switches it off.
+ * Every rank must then make the same sequence of ikf_flow_inverse_gather calls (SPMD). */
+int ikf_flow_set_peers(IkfFlow* flow, int n_ranks, int rank, void* const* gather_bufs, void* const* flag_bufs);
+
+/* ikf_flow_inverse with the gather fused in: this rank's `batch` rows (>= 1) become rows [row0, row0 + batch) of the
+ * gathered tensor [rows_total][gather_ld] that starts `gather_offset` floats into every rank's symmetric allocation.
+ * When the call's work has completed on `stream`, the gathered tensor of THIS rank holds the rows of all ranks.
+ * The caller alternates between two offsets (ping-pong) so that a rank that runs ahead never overwrites a buffer a
+ * peer is still reading. */
+int ikf_flow_inverse_gather(IkfFlow* flow, const float* latent, int latent_ld, const float* cond, int cond_ld, int cond_rows,
+                            int cond_cols, int out_cols, int batch, int clamp, size_t gather_offset, int gather_ld, int row0,
+                            void* stream);
+
 /* Optional: the stored FixedLinearTransform parameters M [ndim_tot][ndim_tot] (row-major, "module_list.0.M", HOST
  * pointer) and logDetM for the forward pass.  Without this call ikf_flow_create's own M = M_inv^-1 (double precision
  * Gauss-Jordan) and log|det M| are used. */
