@@ -303,7 +303,7 @@ def extra_block(args, rank, world, dev, flush, headline_solver):
 
     import ikflow_b200
     from ikflow_b200 import ikflow_solver as solver_mod
-    from ikflow_b200.distributed import all_gather_rows, shard_bounds
+    from ikflow_b200.distributed import PeerGather, all_gather_rows, shard_bounds
 
     extra = {}
     peaks = measured_peaks()
@@ -322,12 +322,28 @@ def extra_block(args, rank, world, dev, flush, headline_solver):
         latent_all = torch.randn(n_total, width, generator=torch.Generator().manual_seed(5)).to(dev)
         poses, latent = poses_all[lo:hi].contiguous(), latent_all[lo:hi].contiguous()
 
+        spg = None
+        if world > 1 and os.environ.get("IKFLOW_B200_GATHER", "fused") == "fused":
+            try:
+                spg = PeerGather(solver, n_total)
+            except Exception:
+                spg = None
+            ok = torch.tensor([1 if spg is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0 and spg is not None:
+                spg.close()
+                spg = None
+
         def step():
+            if spg is not None:
+                return spg.generate_ik_solutions(poses, latent)
             local = solver.generate_ik_solutions(poses, latent=latent)
             return all_gather_rows(local, n_total) if world > 1 else local
 
         p50, mean = time_calls(step, 20, 5, flush)
         p50, mean = reduce_max(p50), reduce_max(mean)
+        if spg is not None:
+            spg.close()
         hp = solver.nn_model.params
         fl = flops_per_solution(hp, width)
         return {
@@ -351,8 +367,21 @@ def extra_block(args, rank, world, dev, flush, headline_solver):
         q, poses_all = headline_solver.robot.sample_joint_angles_and_poses(512, seed=78, return_torch=True, device=dev)
         latent_all = torch.randn(512, 7, generator=torch.Generator().manual_seed(6)).to(dev)
         poses, latent = poses_all[lo:hi].contiguous(), latent_all[lo:hi].contiguous()
-        p50, mean = time_calls(lambda: all_gather_rows(headline_solver.generate_ik_solutions(poses, latent=latent), 512), 20, 5, flush)
+        spg = None
+        try:
+            spg = PeerGather(headline_solver, 512) if os.environ.get("IKFLOW_B200_GATHER", "fused") == "fused" else None
+        except Exception:
+            spg = None
+        ok = torch.tensor([1 if spg is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0 and spg is not None:
+            spg.close()
+            spg = None
+        strong_step = (lambda: spg.generate_ik_solutions(poses, latent)) if spg is not None else (lambda: all_gather_rows(headline_solver.generate_ik_solutions(poses, hi - lo, latent=latent), 512))
+        p50, mean = time_calls(strong_step, 20, 5, flush)
         p50, mean = reduce_max(p50), reduce_max(mean)
+        if spg is not None:
+            spg.close()
         extra["config2_strong_b512"] = {"workload": f"{HEADLINE_MODEL}, batch=512 total", "rows_per_gpu": hi - lo, "n_gpus": world, "scaling": "strong",
                                         "p50_ms": p50, "mean_ms": mean, "value": 512 / (mean * 1e-3), "unit": UNIT,
                                         "note": "a launch streams all weights whatever the row count (B=64: ~0.5 ms): the headline batch does not strong-scale"}
@@ -507,7 +536,7 @@ def main():
 
     import ikflow_b200
     from ikflow_b200 import _lib
-    from ikflow_b200.distributed import all_gather_rows
+    from ikflow_b200.distributed import PeerGather, all_gather_rows
 
     solver, hp = ikflow_b200.get_ik_solver(args.model, synthetic_seed=0)
     precision = solver.nn_model.precision
@@ -518,9 +547,28 @@ def main():
     latent = torch.randn(B, width, generator=torch.Generator().manual_seed(4321 + rank)).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB of L2
 
+    # N > 1: the gather is fused into the kernel's epilogue (peer stores over NVLink + flags, ikflow_b200.distributed.PeerGather);
+    # IKFLOW_B200_GATHER=nccl (or a box without peer access) falls back to one NCCL all-gather per step
+    pg, gather_kind = None, "none (single GPU)"
+    if world > 1 and args.mode == "approx":
+        gather_kind = "nccl all_gather_into_tensor"
+        if os.environ.get("IKFLOW_B200_GATHER", "fused") == "fused":
+            try:
+                pg = PeerGather(solver, B * world)
+                gather_kind = "fused into the flow kernel: peer stores (NVLink P2P) + per-rank flags, no collective"
+            except Exception as e:  # no symmetric memory / no peer access: keep the collective
+                gather_kind += f" (fused gather unavailable: {type(e).__name__}: {str(e)[:120]})"
+        ok = torch.tensor([1 if pg is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks or none
+        if int(ok.item()) == 0 and pg is not None:
+            pg.close()
+            pg = None
+
     def step_resident():
         if args.mode == "exact":  # BASELINE.json configs[2]: thresholds of scripts/benchmark_generate_exact_solutions.py:18-19
             local, _valid = solver.generate_exact_ik_solutions(poses, pos_error_threshold=POS_THR, rot_error_threshold=ROT_THR)
+        elif pg is not None:
+            return pg.generate_ik_solutions(poses, latent)
         else:
             local = solver.generate_ik_solutions(poses, latent=latent)
         return all_gather_rows(local, B * world) if world > 1 else local
@@ -569,9 +617,9 @@ def main():
         if args.mode == "exact":
             sol, _valid = solver.generate_exact_ik_solutions(y, pos_error_threshold=POS_THR, rot_error_threshold=ROT_THR)
         else:
-            sol = solver.generate_ik_solutions(y)  # draws its own latent on the device, like the reference
+            sol = pg.generate_ik_solutions(y) if pg is not None else solver.generate_ik_solutions(y)  # draws its own latent on the device, like the reference
         if world > 1:
-            sol = all_gather_rows(sol, B * world)[rank * B : (rank + 1) * B]
+            sol = (sol if pg is not None else all_gather_rows(sol, B * world))[rank * B : (rank + 1) * B]
         out_host.copy_(sol, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -597,6 +645,8 @@ def main():
         kernel_ms, _ = time_calls(lambda: solver.generate_ik_solutions(poses, latent=latent), 50, 3, flush)
     kernel_name = solver.nn_model.last_kernel()
 
+    if pg is not None:
+        pg.close()
     extra = None
     if not args.no_extra and args.model == HEADLINE_MODEL and args.mode == "approx":
         extra = extra_block(args, rank, world, dev, flush, solver)
@@ -618,7 +668,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(poses_host.numel() * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e2e_steps},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "gather": gather_kind,
             "roofline": {
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,

@@ -679,13 +679,6 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   }
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) return fail(IKF_ECUDA, "%s: launch failed: %s", name, cudaGetErrorString(e));
-  if (gather) {
-    // consumer side of the fused gather: stream-ordered wait for the shards of all ranks (one warp polling flags)
-    umma::wait_peers_kernel<<<1, 32, 0, st>>>(flow->peer_flag[flow->rank], flow->n_ranks, p.peer_seq, p.status, p.status_host);
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(IKF_ECUDA, "%s: wait_peers launch failed: %s", name, cudaGetErrorString(e));
-  }
   if (capturing == cudaStreamCaptureStatusNone) {
     e = cudaEventRecord(flow->done, st);
     if (e != cudaSuccess) return fail(IKF_ECUDA, "%s: cudaEventRecord failed: %s", name, cudaGetErrorString(e));

@@ -1346,6 +1346,21 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
       if (old + 1u == p.peer_count_target) {
         __threadfence_system();
         for (int r = 0; r < p.n_peers; ++r) st_release_sys(p.peer_flag[r] + p.peer_rank, p.peer_seq);
+        // ... and, as the last CTA alive, waits for the shards of the other ranks: when this kernel ends, this rank's
+        // gathered tensor is complete -- no second launch, no collective.  (Every rank publishes before it waits, so the
+        // ranks cannot wait for each other in a circle; the wait is bounded like all others.)
+        const uint32_t* mine = p.peer_flag[p.peer_rank];
+        const long long t0 = clock64();
+        for (int r = 0; r < p.n_peers; ++r) {
+          uint32_t spins = 0;
+          while ((int32_t)(ld_acquire_sys(mine + r) - p.peer_seq) < 0) {
+            if (++spins > 32) __nanosleep(40);
+            if ((spins & 1023u) == 0 && clock64() - t0 > 6000000000LL) {  // ~3 s: a peer never published
+              report_timeout(p.status, p.status_host, launch_id);
+              break;
+            }
+          }
+        }
       }
     }
   }
@@ -1358,22 +1373,6 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
 }
 
 #undef IKF_CS
-
-// Fused gather, consumer side: returns (in stream order) when every rank's shard of sequence number `seq` has arrived in
-// this rank's gathered buffer.  One warp, lane r polls rank r's flag; bounded like every other wait of the library.
-__global__ void __launch_bounds__(32) wait_peers_kernel(const uint32_t* flags, int n_peers, uint32_t seq, uint32_t* status, uint32_t* status_host) {
-  const int r = threadIdx.x;
-  if (r >= n_peers) return;
-  const long long t0 = clock64();
-  uint32_t spins = 0;
-  while ((int32_t)(ld_acquire_sys(flags + r) - seq) < 0) {
-    if (++spins > 64) __nanosleep(100);
-    if ((spins & 1023u) == 0 && clock64() - t0 > 6000000000LL) {  // ~3 s: a peer never published
-      report_timeout(status, status_host, seq);
-      return;
-    }
-  }
-}
 
 }  // namespace umma
 }  // namespace ikf

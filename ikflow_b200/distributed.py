@@ -86,9 +86,9 @@ class PeerGather:
 
     Every rank allocates the SAME symmetric buffer -- two gathered tensors ``[n_total, ndof]`` (ping-pong) -- plus a flag
     array, and maps its peers' copies (``torch.distributed._symmetric_memory``: CUDA VMM handles exchanged over the
-    process group, NVLink P2P).  ``generate_ik_solutions`` then is ONE flow launch whose final epilogue stores this rank's
-    joint angles into the gathered tensor of every rank, followed by a one-warp kernel that waits for the other ranks'
-    shards: no NCCL call on the critical path.  All ranks must call it the same number of times (SPMD), each with
+    process group, NVLink P2P).  ``generate_ik_solutions`` then is ONE flow launch: its final epilogue stores this rank's
+    joint angles into the gathered tensor of every rank, its last CTA raises this rank's flag everywhere and waits for the
+    other ranks' flags -- when the kernel ends the gathered tensor is complete; no NCCL call, no second launch.  All ranks must call it the same number of times (SPMD), each with
     the rows ``shard_bounds(n_total, rank, world)`` of the batch; the returned tensor is valid until the call after the
     next one.
     """

@@ -136,8 +136,8 @@ int ikf_flow_forward(IkfFlow* flow, const float* x, int x_ld, const float* cond,
  * The reference has no multi-GPU path; BASELINE's north star shards the batch over up to 8 GPUs and gathers the joint
  * angles with one NCCL all-gather.  The fused alternative removes the collective from the critical path: the kernel's
  * final epilogue stores its rows into the gathered buffer of EVERY rank (peer-mapped device pointers, NVLink stores) and
- * the last CTA raises this rank's flag on every rank; ikf_flow_inverse_gather then queues a one-warp kernel that waits
- * (stream-ordered) for the flags of all ranks.
+ * the last CTA to finish raises this rank's flag on every rank and then waits for the flags of the other ranks, so that
+ * the end of the kernel IS the end of the gather: no second launch.
  *
  * ikf_flow_set_peers: gather_bufs[r] = base of rank r's symmetric allocation as mapped into THIS process (cudaIpc /
  * torch symmetric memory / cuMem), flag_bufs[r] = rank r's flag array [n_ranks] uint32 (zero-initialised by its owner
