@@ -488,7 +488,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra block (BASELINE configs 1, 3, 4, 5)")
-    ap.add_argument("--precision", default=None, choices=["bf16x3", "fp16x3", "bf16x1"])
+    ap.add_argument("--precision", default=None, choices=["auto", "bf16x3", "fp16x3", "bf16x1"])
     ap.add_argument("--mode", default="approx", choices=["approx", "exact"],
                     help="approx = generate_ik_solutions (headline); exact = generate_exact_ik_solutions (flow + LM refinement)")
     args = ap.parse_args()
@@ -539,7 +539,7 @@ def main():
     from ikflow_b200.distributed import PeerGather, all_gather_rows
 
     solver, hp = ikflow_b200.get_ik_solver(args.model, synthetic_seed=0)
-    precision = solver.nn_model.precision
+    precision = solver.nn_model.effective_precision(dev)
     robot = solver.robot
     width = solver.network_width
     B = args.batch

@@ -15,9 +15,11 @@ IKF_OK = 0
 IKF_ESTATUS = -5
 IKF_STATUS_NONFINITE = 1
 IKF_STATUS_SYNC_TIMEOUT = 2
+IKF_STATUS_RANGE = 4
 IKF_PRECISION_BF16X3 = 0
 IKF_PRECISION_BF16X1 = 1
 IKF_PRECISION_FP16X3 = 2
+IKF_PRECISION_AUTO = 3
 IKF_MAX_WIDTH = 16
 IKF_MAX_LINKS = 16
 IKF_MAX_DOF = 8
@@ -49,6 +51,7 @@ PROTOTYPES = {
     "ikf_flow_set_forward_tables": (c_int, [c_void_p, c_void_p, c_float]),
     "ikf_flow_status": (c_int, [c_void_p, c_void_p, POINTER(c_uint32)]),
     "ikf_flow_poll_status": (c_int, [c_void_p, POINTER(c_uint32)]),
+    "ikf_flow_precision": (c_int, [c_void_p]),
     "ikf_flow_last_kernel": (c_char_p, [c_void_p]),
     "ikf_flow_last_cluster": (c_int, [c_void_p]),
     "ikf_flow_debug_trace": (c_int, [c_void_p, c_void_p, c_int]),

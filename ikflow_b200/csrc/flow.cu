@@ -65,7 +65,7 @@ static bool desc_ok(const IkfFlowDesc* d) {
   if (d->coeff_fn_config < 1 || d->coeff_fn_config > 4) return false;
   if (d->hidden < 64 || d->hidden % 64 != 0 || d->hidden > 2048) return false;
   if (d->ndof < 1 || d->ndof > d->ndim_tot) return false;
-  if (d->precision != IKF_PRECISION_BF16X3 && d->precision != IKF_PRECISION_BF16X1 && d->precision != IKF_PRECISION_FP16X3) return false;
+  if (d->precision < IKF_PRECISION_BF16X3 || d->precision > IKF_PRECISION_AUTO) return false;
   const int s1 = d->ndim_tot / 2, s2 = d->ndim_tot - s1;
   if (s2 + d->dim_cond > kPad || 2 * s2 > kPad) return false;
   return true;
@@ -213,7 +213,8 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
     }
   }
   f->engine = engine;
-  const bool f16 = desc->precision == IKF_PRECISION_FP16X3;
+  if (f->desc.precision == IKF_PRECISION_AUTO) f->desc.precision = engine ? IKF_PRECISION_FP16X3 : IKF_PRECISION_BF16X3;
+  const bool f16 = f->desc.precision == IKF_PRECISION_FP16X3;
   if (f16 && !engine) {
     delete f;
     return fail(IKF_EINVAL, "ikf_flow_create: IKF_PRECISION_FP16X3 is implemented by the tcgen05 engine only (hidden %% 128 == 0, hidden <= 1024, coeff_fn_config >= 2)");
@@ -507,7 +508,7 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   FlowParams& p = f->base;
   std::memset(&p, 0, sizeof(p));
   p.W = W; p.s1 = s1; p.s2 = s2; p.dim_cond = desc->dim_cond; p.nb_nodes = nb; p.n_big = n_big; p.H = H; p.NT = NT;
-  p.ndof = desc->ndof; p.precision = desc->precision;
+  p.ndof = desc->ndof; p.precision = f->desc.precision;
   p.clamp_scale = (float)((double)desc->rnvp_clamp * 0.636);
   p.big_w = (const __nv_bfloat16*)(base + off_big);
   p.small = (const float*)(base + off_small);
@@ -567,9 +568,13 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   std::lock_guard<std::mutex> lock(flow->mu);
   // A previous launch that gave up on an inter-CTA wait has written into the mapped status word by now (or will have
   // by the time its stream is synchronised): refuse to build on its garbage.  No synchronisation: a plain host read.
-  if (flow->status_host[0] & IKF_STATUS_SYNC_TIMEOUT) {
-    const uint32_t id = flow->status_host[1];
-    flow->status_host[0] &= ~IKF_STATUS_SYNC_TIMEOUT;
+  if (flow->status_host[0] & (IKF_STATUS_SYNC_TIMEOUT | IKF_STATUS_RANGE)) {
+    const uint32_t bits = flow->status_host[0], id = flow->status_host[1];
+    flow->status_host[0] &= ~(IKF_STATUS_SYNC_TIMEOUT | IKF_STATUS_RANGE);
+    if (bits & IKF_STATUS_RANGE)
+      return fail(IKF_ESTATUS, "%s: an earlier launch on this handle left the fp16 range (IKF_STATUS_RANGE: a hidden activation "
+                  "exceeded 65504 in magnitude or was NaN): its output is invalid.  Create the flow with IKF_PRECISION_BF16X3 "
+                  "(IKFLOW_B200_PRECISION=bf16x3), which has the exponent range of fp32", name);
     return fail(IKF_ESTATUS, "%s: an earlier launch on this handle (id %u) timed out waiting for another CTA "
                 "(IKF_STATUS_SYNC_TIMEOUT): its output is invalid.  The usual cause is a kernel of another process or "
                 "stream holding SMs, so that the cooperative launch could not make progress", name, id);
@@ -783,6 +788,8 @@ int ikf_flow_debug_trace(IkfFlow* flow, unsigned long long* dev_stamps, int n_la
   flow->trace_layers = n_layers;
   return IKF_OK;
 }
+
+int ikf_flow_precision(IkfFlow* flow) { return flow ? flow->desc.precision : IKF_EINVAL; }
 
 const char* ikf_flow_last_kernel(IkfFlow* flow) { return flow ? flow->last_kernel : ""; }
 

@@ -236,6 +236,14 @@ __device__ __forceinline__ void report_nonfinite(uint32_t* status, uint32_t* sta
   }
 }
 
+__device__ __forceinline__ void report_range(uint32_t* status, uint32_t* status_host) {
+  atomicOr(status, IKF_STATUS_RANGE);
+  if (status_host != nullptr) {
+    volatile uint32_t* h = status_host;
+    h[0] = h[0] | IKF_STATUS_RANGE;
+  }
+}
+
 // Wait until *flag has reached `expected` (wrap-safe).  Gives up (and makes every later wait of this launch give up)
 // after about a second: the results are then garbage and IKF_STATUS_SYNC_TIMEOUT is reported, but the GPU is not hung.
 // The caller issues the acquire fence.

@@ -360,7 +360,7 @@ __device__ __forceinline__ void jit_chunk_load(uint32_t stage_a, uint32_t w1off,
 }
 template <int KB, int APLANE, bool F16>
 __device__ __forceinline__ void jit_chunk_compute(uint32_t stage_a, int j, int lane, const float (&x)[4][KB],
-                                                  const uint64_t (&w)[KB + 1][2]) {
+                                                  const uint64_t (&w)[KB + 1][2], uint32_t* status, uint32_t* status_host) {
   const int q = lane >> 2, fq = lane & 3;
   const int f0 = 16 * j + 4 * fq;
   uint64_t acc[4][2];
@@ -375,6 +375,7 @@ __device__ __forceinline__ void jit_chunk_compute(uint32_t stage_a, int j, int l
       acc[rr][1] = ffma2(xk, w[k][1], acc[rr][1]);
     }
   }
+  float vmax = 0.f;  // fp16x3: largest magnitude seen (the fp16 head of anything above 65504 is inf); checked once per chunk
 #pragma unroll
   for (int rr = 0; rr < 4; ++rr) {
     uint32_t hb[2], lb[2];
@@ -383,12 +384,14 @@ __device__ __forceinline__ void jit_chunk_compute(uint32_t stage_a, int j, int l
       float a0, a1;
       unpack2(acc[rr][c], a0, a1);
       a0 = leaky(a0), a1 = leaky(a1);
+      if (F16) vmax = fmaxf(vmax, fmaxf(fabsf(a0), fabsf(a1)));
       split_pair<F16>(a0, a1, hb[c], lb[c]);
     }
     const uint32_t off = tile_off_bytes(q + 8 * rr, f0);
     sts64u(stage_a + kWChunkU + off, hb[0], hb[1]);
     sts64u(stage_a + kWChunkU + APLANE + off, lb[0], lb[1]);
   }
+  if (F16 && vmax > 65504.f) report_range(status, status_host);
 }
 
 // Exchanged first layer (kernels without the just-in-time version), one tile of 32 rows x 16 features per call, same
@@ -398,7 +401,7 @@ __device__ __forceinline__ void jit_chunk_compute(uint32_t stage_a, int j, int l
 // broadcast 128-bit loads of the inputs (a quarter warp per bank phase): 7.2 us per subnet at 128 rows.
 template <int KB, int APLANE, bool F16>
 __device__ __forceinline__ void first_layer_tile(uint32_t w_a, uint32_t b_a, const float (&x)[4][KB], int rb, int fb, int lane,
-                                                 uint8_t* dst_chunk0, int chunk_bytes) {
+                                                 uint8_t* dst_chunk0, int chunk_bytes, uint32_t* status, uint32_t* status_host) {
   const int q = lane >> 2, fq = lane & 3;
   const int f0 = fb * 16 + 4 * fq;  // feature inside the CTA's 128
   uint64_t acc[4][2];
@@ -417,6 +420,7 @@ __device__ __forceinline__ void first_layer_tile(uint32_t w_a, uint32_t b_a, con
     }
   }
   uint8_t* dst = dst_chunk0 + (size_t)(f0 >> 6) * chunk_bytes;
+  float vmax = 0.f;  // see jit_chunk_compute
 #pragma unroll
   for (int rr = 0; rr < 4; ++rr) {
     uint32_t hb[2], lb[2];
@@ -425,12 +429,14 @@ __device__ __forceinline__ void first_layer_tile(uint32_t w_a, uint32_t b_a, con
       float a0, a1;
       unpack2(acc[rr][c], a0, a1);
       a0 = leaky(a0), a1 = leaky(a1);
+      if (F16) vmax = fmaxf(vmax, fmaxf(fabsf(a0), fabsf(a1)));
       split_pair<F16>(a0, a1, hb[c], lb[c]);
     }
     const uint32_t off = tile_off_bytes(rb * 32 + q + 8 * rr, f0 & 63);
     stg64(dst + off, hb[0], hb[1]);
     stg64(dst + APLANE + off, lb[0], lb[1]);
   }
+  if (F16 && vmax > 65504.f) report_range(status, status_host);
 }
 
 template <int RT, bool JIT = false, bool F16 = false>
@@ -438,6 +444,15 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
   using C = Cfg<RT, JIT>;
   constexpr int kStages = C::kStages;
   constexpr int G = C::kGroups, ER = C::kEpiRows, ET = C::kEpiThreads;
+  // Accumulator tiles per hidden layer: k-chunk i goes to tile i % kAcc, the epilogue adds the tiles in a fixed order.
+  // The tensor core TRUNCATES its fp32 accumulator after every k16 step (a CPU emulation with round-toward-zero reproduces
+  // the measured errors, scripts/precision_study.py), a bias that grows with the number of sequential steps: 64 per layer
+  // with one tile.  bf16x3 does not notice (its 16-bit operands dominate its error); fp16x3, whose operands carry 22 bits,
+  // is limited by exactly this, so it spreads the chunks over 4 tiles (2 at 128 rows: TMEM has 512 columns) and sums
+  // them in fp32 round-to-nearest.
+  constexpr int kAcc = F16 ? (RT == 128 ? 2 : 4) : 1;
+  constexpr int kTmemColsK = kAcc * C::kAccCols <= 32 ? 32 : (kAcc * C::kAccCols <= 64 ? 64 : (kAcc * C::kAccCols <= 128 ? 128 : (kAcc * C::kAccCols <= 256 ? 256 : 512)));
+  static_assert(kAcc * C::kAccCols <= 512 && C::kMmaWarps == 1, "TMEM has 512 columns; the tiles are dealt by chunk index");
   extern __shared__ uint8_t smem_raw[];
   Smem<RT, JIT>& sm = *reinterpret_cast<Smem<RT, JIT>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -479,7 +494,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
   }
   if (warp == C::kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)),
-                 "n"(C::kTmemCols)
+                 "n"(kTmemColsK)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -537,7 +552,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
       const uint32_t use = ((uint32_t)g * (uint32_t)p.n_big * (uint32_t)KCH + (uint32_t)i) / kStages;
       if (use > 0) mbar_wait(&sm.empty[st], (use - 1) & 1);
       if (tb) tb[32 + (i >> 1)] = clock64();
-      if (!(p.debug & 2048)) jit_chunk_compute<KB, C::kAPlane, F16>(stage_a, j, lane, xx, w);
+      if (!(p.debug & 2048)) jit_chunk_compute<KB, C::kAPlane, F16>(stage_a, j, lane, xx, w, p.status, p.status_host);
       if (tb) tb[48 + (i >> 1)] = clock64();
       if (!(p.debug & 1024)) fence_proxy_async_smem();  // generic-proxy writes -> the tensor core's (async proxy) reads
       bar_gen_group(grp);
@@ -847,8 +862,8 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
       const uint64_t d_wh0 = make_desc(smem_u32(sm.ring[0])), d_wl0 = make_desc(smem_u32(sm.ring[0]) + kWPlaneU);
       const uint64_t d_a0 = make_desc(smem_u32(sm.ring[0]) + kWChunkU);
       const int mw = warp - C::kMmaWarp;  // this warp's chunks: i = mw (mod kMmaWarps), its accumulator tile: mw
-      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0) + (uint32_t)(mw * C::kAccCols);
-      const uint32_t tmem_u2 = tmem_u + (F16 ? RT : 0);  // fp16x3: the scaled correction terms have their own accumulator
+      const uint32_t tmem_u0 = __shfl_sync(0xffffffffu, tmem, 0);
+      constexpr uint32_t kCorrOff = F16 ? RT : 0;  // fp16x3: the scaled correction terms have their own accumulator
       for (int g = 0; g < total_steps; ++g) {
         for (int l = 0; l < p.n_big; ++l) {
           if (layers > 0) mbar_wait(&sm.dempty, (layers - 1) & 1);  // the epilogue has drained the accumulators
@@ -866,10 +881,11 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
               if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 16 + i);
               const uint64_t dwh = d_w0 + (uint64_t)(sw * (kWChunkU >> 4)), da = d_as0 + (uint64_t)(sa * (C::kAChunk >> 4));
               if (elect_one()) {
+                const uint32_t tmem_u = tmem_u0 + (uint32_t)((i % kAcc) * C::kAccCols);  // accumulator tile of this chunk
                 if (x3)
-                  mma_chunk_x3(tmem_u, tmem_u2, idesc2, idesc, dwh, dwh + (uint64_t)(kWPlaneU >> 4), da, i >= C::kMmaWarps);
+                  mma_chunk_x3(tmem_u, tmem_u + kCorrOff, idesc2, idesc, dwh, dwh + (uint64_t)(kWPlaneU >> 4), da, i >= kAcc);
                 else
-                  mma_chunk_x1(tmem_u, idesc, dwh, da, i >= C::kMmaWarps);
+                  mma_chunk_x1(tmem_u, idesc, dwh, da, i >= kAcc);
                 // both stages are free once these MMAs have read them (clusters: the weight stage is refilled by every CTA)
                 if (p.cluster > 1) mma_commit_multicast(&sm.wempty[sw], (uint16_t)((1u << p.cluster) - 1u)); else mma_commit(&sm.wempty[sw]);
                 mma_commit(&sm.aempty[sa]);
@@ -892,10 +908,12 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
                 if (p.trace != nullptr && lane == 0 && i0 + s < 16) trace_clk(p, g * 4 + l, 16 + i0 + s);
                 constexpr uint64_t kStageOff = (uint64_t)(C::kStage >> 4);  // stage offset in the 16-byte address field
                 if (elect_one()) {
+                  static_assert(kStages % kAcc == 0, "the tile of a stage must not depend on the group");
+                  const uint32_t tmem_u = tmem_u0 + (uint32_t)((s % kAcc) * C::kAccCols);  // accumulator tile of this chunk
                   if (x3)
-                    mma_chunk_x3(tmem_u, tmem_u2, idesc2, idesc, d_wh0 + s * kStageOff, d_wl0 + s * kStageOff, d_a0 + s * kStageOff, (i0 + s) >= C::kMmaWarps);
+                    mma_chunk_x3(tmem_u, tmem_u + kCorrOff, idesc2, idesc, d_wh0 + s * kStageOff, d_wl0 + s * kStageOff, d_a0 + s * kStageOff, (i0 + s) >= kAcc);
                   else
-                    mma_chunk_x1(tmem_u, idesc, d_wh0 + s * kStageOff, d_a0 + s * kStageOff, (i0 + s) >= C::kMmaWarps);
+                    mma_chunk_x1(tmem_u, idesc, d_wh0 + s * kStageOff, d_a0 + s * kStageOff, (i0 + s) >= kAcc);
                   // the stage is free once these MMAs have read it (clusters: tell every CTA that refills it)
                   if (p.cluster > 1) mma_commit_multicast(&sm.empty[s], (uint16_t)((1u << p.cluster) - 1u)); else mma_commit(&sm.empty[s]);
                 }
@@ -1032,7 +1050,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
 #pragma unroll
               for (int ti = 0; ti < kTilesPerWarp; ++ti)
                 first_layer_tile<KB, C::kAPlane, F16>(sp_a + (kSmFirstW - C::kSmShift) * 4, sp_a + (kSmFirstB - C::kSmShift) * 4, x, rb, fb0 + ti,
-                                                 lane, dst0, C::kAChunk);
+                                                 lane, dst0, C::kAChunk, p.status, p.status_host);
             };
             if (kin <= 12) run(std::integral_constant<int, 12>{});
             else run(std::integral_constant<int, kPad>{});
@@ -1073,9 +1091,10 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
               if (tid == 0) trace_ev(p, g * 4 + l - 1, 7);
 #pragma unroll
               for (int c0 = 0; c0 < ER; c0 += 32) {
-                // the tiles of the two MMA warps (even / odd k-chunks), added in a fixed order
+                // the accumulator tiles (k-chunks i = m mod kAcc), added in a fixed order
 #pragma unroll
-                for (int m = 0; m < C::kMmaWarps; ++m) {
+                for (int m = 0; m < kAcc; ++m) {
+                  if (m >= KCH) break;  // a layer of fewer chunks than tiles (hidden = 128) leaves the rest untouched
                   float tmp[32], tmp2[32];
                   tmem_ld32(taddr + m * C::kAccCols + row0 + c0, tmp);  // bf16x3: W_head*A_head + W_tail*A_head; fp16x3: W_head*A_head
                   if (x3) {
@@ -1104,12 +1123,16 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
               const int buf = axchg & 1;
               uint8_t* dst = act_slot + ((size_t)buf * NT + t) * kAStrideU + (size_t)sub * C::kAChunk;
               const int kf8 = kf & ~7;
+              float pub_max = 0.f;  // fp16x3: largest magnitude published (checked once, after the stores)
               if (!(l == 0 && tiled_first))  // (the tiled first layer has stored its output already)
 #pragma unroll
               for (int r0 = 0; r0 < ER; r0 += 8) {
                 uint32_t wd[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) wd[i] = split_one<F16>(v[r0 + i]);  // head in the low half, tail in the high half
+                for (int i = 0; i < 8; ++i) {
+                  if (F16) pub_max = fmaxf(pub_max, fabsf(v[r0 + i]));
+                  wd[i] = split_one<F16>(v[r0 + i]);  // head in the low half, tail in the high half
+                }
                 // before: lane j8 (feature kf8 + j8) holds rows r0..r0+7; after: lane j8 holds row r0 + j8, features kf8..kf8+7
 #pragma unroll
                 for (int st = 4; st >= 1; st >>= 1) {
@@ -1136,6 +1159,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
                           __byte_perm(wd[4], wd[5], 0x7632), __byte_perm(wd[6], wd[7], 0x7632));
                 }
               }
+              if (F16 && pub_max > 65504.f) report_range(p.status, p.status_host);  // the fp16 head of such a value is inf
               if constexpr (JIT) fence_proxy_async_smem();  // the tensor core reads the own chunks through the async proxy
               bar_epi<ET>();
               if constexpr (JIT) {
@@ -1368,7 +1392,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
   __syncthreads();
   if (p.cluster > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == C::kMmaWarp) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(C::kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemColsK) : "memory");
   }
 }
 

@@ -22,12 +22,12 @@ class FlowModel:
         joint_limits: Sequence[Tuple[float, float]],
         dim_cond: int,
         ndim_tot: int,
-        precision: str = "bf16x3",
+        precision: str = "auto",
     ):
         assert params.coupling_layer == "glow", "only the GLOW coupling block is implemented (all released models)"
         assert not getattr(params, "sigmoid_on_output", False), "sigmoid_on_output is not used by any released model"
         assert params.permute_random_enabled, "permute_random_enabled=False is not supported"
-        assert precision in ("bf16x3", "bf16x1", "fp16x3")
+        assert precision in ("auto", "bf16x3", "bf16x1", "fp16x3")
         self.params = params
         self.ndim_tot = int(ndim_tot)
         self.dim_cond = int(dim_cond)
@@ -96,7 +96,7 @@ class FlowModel:
     def _desc(self) -> _lib.IkfFlowDesc:
         return _lib.IkfFlowDesc(
             self.ndim_tot, self.dim_cond, self.nb_nodes, self.coeff_fn_config, self.hidden, self.ndof, self.rnvp_clamp,
-            {"bf16x3": _lib.IKF_PRECISION_BF16X3, "bf16x1": _lib.IKF_PRECISION_BF16X1, "fp16x3": _lib.IKF_PRECISION_FP16X3}[self.precision],
+            {"bf16x3": _lib.IKF_PRECISION_BF16X3, "bf16x1": _lib.IKF_PRECISION_BF16X1, "fp16x3": _lib.IKF_PRECISION_FP16X3, "auto": _lib.IKF_PRECISION_AUTO}[self.precision],
         )
 
     def flat_weights(self) -> np.ndarray:
@@ -239,6 +239,11 @@ class FlowModel:
         word = ctypes.c_uint32(0)
         _lib.check(_lib.lib().ikf_flow_poll_status(self._handle(dev), ctypes.byref(word)), "ikf_flow_poll_status")
         return int(word.value)
+
+    def effective_precision(self, device=None) -> str:
+        """The operand format in use: resolves ``"auto"`` (fp16x3 on the tcgen05 engine, bf16x3 on the mma.sync engine)."""
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        return {0: "bf16x3", 1: "bf16x1", 2: "fp16x3"}[int(_lib.lib().ikf_flow_precision(self._handle(dev)))]
 
     def last_kernel(self, device=None) -> str:
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())

@@ -141,7 +141,7 @@ def make_synthetic_state_dict(
     return sd
 
 
-DEFAULT_PRECISION = "bf16x3"
+DEFAULT_PRECISION = "auto"
 
 
 def glow_cNF_model(params: IkflowModelParameters, robot, dim_cond: int, ndim_tot: int, precision: Optional[str] = None):
@@ -153,9 +153,11 @@ def glow_cNF_model(params: IkflowModelParameters, robot, dim_cond: int, ndim_tot
     FixedLinearTransform matrices and the permutation tables) arrive through ``load_state_dict`` exactly as in the
     reference.
 
-    ``precision``: operand format of the hidden-layer tensor-core products, ``"bf16x3"`` / ``"fp16x3"`` (parity grade, see
-    ``include/ikflow_b200.h``) or ``"bf16x1"`` (fast, NOT parity grade); default ``IKFLOW_B200_PRECISION`` or
-    ``DEFAULT_PRECISION``.
+    ``precision``: operand format of the hidden-layer tensor-core products (``include/ikflow_b200.h``): ``"auto"`` (default:
+    ``"fp16x3"`` where the tcgen05 engine runs the model, ``"bf16x3"`` otherwise), ``"fp16x3"`` (fp32-grade: as close to the
+    fp32 reference as two fp32 implementations are to each other; hidden activations must stay inside the fp16 range),
+    ``"bf16x3"`` (16 operand bits, the exponent range of fp32, 3 % faster) or ``"bf16x1"`` (fast, NOT parity grade);
+    ``IKFLOW_B200_PRECISION`` overrides the default.
     """
     import os
 

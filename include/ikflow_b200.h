@@ -38,7 +38,7 @@ extern "C" {
 #define IKF_ECUDA (-2)    /* CUDA runtime error (see ikf_last_error) */
 #define IKF_ENOMEM (-3)   /* device allocation failed */
 #define IKF_EDEVICE (-4)  /* device is not an sm_100 part / kernel image not loadable */
-#define IKF_ESTATUS (-5)  /* an EARLIER launch on the handle reported IKF_STATUS_SYNC_TIMEOUT (its output is invalid) */
+#define IKF_ESTATUS (-5)  /* an EARLIER launch on the handle reported IKF_STATUS_SYNC_TIMEOUT or IKF_STATUS_RANGE (its output is invalid) */
 
 /* status bits reported by ikf_flow_status / ikf_flow_poll_status */
 #define IKF_STATUS_NONFINITE 1u    /* an output was not finite (NaN / inf inputs propagate, as in the reference) */
@@ -46,6 +46,10 @@ extern "C" {
                                       launch spin on each other's flags, so a co-tenant kernel that holds SMs can stall
                                       it; the kernel then gives up instead of hanging the GPU, writes this bit into
                                       mapped host memory, and the NEXT call on the handle fails with IKF_ESTATUS */
+
+#define IKF_STATUS_RANGE 4u        /* IKF_PRECISION_FP16X3 only: a hidden activation left the fp16 range (|x| > 65504): the
+                                      outputs of that launch are invalid (NaN); like a timeout, the NEXT call on the handle
+                                      fails with IKF_ESTATUS.  Use IKF_PRECISION_BF16X3 for such weights */
 
 #define IKF_MAX_WIDTH 16  /* dim_latent_space */
 #define IKF_MAX_LINKS 16  /* links on the kinematic chain (fixed + actuated) */
@@ -79,6 +83,9 @@ typedef struct {
  * below 65504 in magnitude (they are O(1) for a trained network); beyond it outputs are NaN and IKF_STATUS_NONFINITE
  * is raised.  tcgen05 engine only. */
 #define IKF_PRECISION_FP16X3 2
+/* AUTO: the most faithful format the engine of this model offers -- FP16X3 on the tcgen05 engine, BF16X3 on the mma.sync
+ * engine (hidden sizes that are not a multiple of 128, or > 1024).  ikf_flow_precision() tells which. */
+#define IKF_PRECISION_AUTO 3
 
 /* ---- flow --------------------------------------------------------------------------------------------------------
  * ikf_flow_create: replaces glow_cNF_model(...) + nn_model.load_state_dict(...) (ikflow/model.py:291-356,
@@ -165,6 +172,9 @@ int ikf_flow_status(IkfFlow* flow, void* stream, uint32_t* status_out);
 /* The same bits WITHOUT synchronising: reads the mirror the kernels keep in mapped host memory (complete for every
  * launch whose stream has been synchronised; may already show a launch still in flight).  Does not clear. */
 int ikf_flow_poll_status(IkfFlow* flow, uint32_t* status_out);
+
+/* The operand format in use (IKF_PRECISION_*; resolves IKF_PRECISION_AUTO). */
+int ikf_flow_precision(IkfFlow* flow);
 
 /* Name of the kernel the last launch on this handle used (for benchmark / profile bookkeeping). */
 const char* ikf_flow_last_kernel(IkfFlow* flow);

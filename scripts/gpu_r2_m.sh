@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/m_build.log 2>&1
+timeout 600 python scripts/precision_gpu.py 256 > gpurun_out/m_precision.log 2>&1
+timeout 900 python -m pytest tests -m gpu -q --tb=short > gpurun_out/m_tests.log 2>&1
+for prec in bf16x3 fp16x3; do
+IKFLOW_B200_PRECISION=$prec timeout 300 python scripts/time_flow.py panda__full__lp191_5.25m 512 1024 2048 8192 >> gpurun_out/m_time.jsonl 2> /dev/null
+done
+echo done
