@@ -80,7 +80,8 @@ def test_exact_solutions_match_oracle_solver_with_injected_latents(panda_solver,
     assert (valid == ref_valid).float().mean() > 0.98
     both = valid & ref_valid
     if both.any():
-        assert (sol[both] - ref_sol[both]).abs().max(dim=1).values.median() < 1e-4
+        dq = (sol[both] - ref_sol[both]).abs().max(dim=1).values
+        assert dq.median() < 1e-4 and dq.max() < 4e-3, (dq.median(), dq.max())  # max: see tests/test_gpu_reference_fixtures.py
         pe, re = jk.pose_error(jk.PANDA, sol[valid], poses[valid])
         assert (pe < 1e-3 + 2e-6).all() and (re < 1e-2 + 2e-5).all()
 
