@@ -88,6 +88,7 @@ static size_t subnet_weight_count(const IkfFlowDesc* d, int in_dim, int out_dim)
 // operand, and the lock step of the two teams only adds jitter); clusters of 4 are never better than 2.
 constexpr int kDefaultCluster = 2;
 constexpr int kDefaultClusterJit = 1;
+constexpr bool kDefaultKSplit = true;
 
 struct IkfFlow {
   IkfFlowDesc desc;
@@ -130,7 +131,7 @@ struct IkfFlow {
     size_t smem = 0;
     const char* name = "";
     int max_slots_cs[5] = {0, 0, 0, 0, 0};  // [cs]: team slots that are co-resident when launched in clusters of cs CTAs (cs = 2, 4)
-  } kern[4];
+  } kern[5];  // [4]: k-split pairs (64-row groups shared by two CTAs per feature tile; tcgen05 only)
   // tcgen05 engine: CTAs per cluster for the weight multicast across teams (1 = off); IKFLOW_B200_CLUSTER overrides
   // fused gather (ikf_flow_set_peers): peer-mapped gathered buffers / flag arrays of every rank of the node
   int n_ranks = 0, rank = 0;
@@ -138,6 +139,9 @@ struct IkfFlow {
   uint32_t* peer_flag[ikf::kMaxPeers] = {};
   uint32_t peer_seq = 0, peer_count_total = 0;
   int cluster_pref = kDefaultCluster, cluster_pref_jit = kDefaultClusterJit;
+  // k-split pairs for batches of up to ks_slots_max x 64 rows (IKFLOW_B200_KSPLIT=0|1 overrides the default)
+  bool ksplit = kDefaultKSplit;
+  int ks_slots_max = 0;
   bool cluster_ok = true;  // cleared if the driver refuses a cooperative launch with clusters
 };
 
@@ -446,16 +450,20 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
     f->kern[1] = {(const void*)umma::flow_inverse_umma_kernel<64, false, true>, umma::Cfg<64>::kThreads, f->smem64, "ikf::umma::flow_inverse_umma_kernel<64,false,true>"};
     f->kern[2] = {(const void*)umma::flow_inverse_umma_kernel<128, false, true>, umma::Cfg<128>::kThreads, f->smem128, "ikf::umma::flow_inverse_umma_kernel<128,false,true>"};
     f->kern[3] = {(const void*)umma::flow_inverse_umma_kernel<32, true, true>, umma::Cfg<32, true>::kThreads, f->smem32j, "ikf::umma::flow_inverse_umma_kernel<32,true,true>"};
+    f->kern[4] = {(const void*)umma::flow_inverse_umma_kernel<32, false, true, true>, umma::Cfg<32, false, true>::kThreads, sizeof(umma::Smem<32, false, true>) + 1024, "ikf::umma::flow_inverse_umma_kernel<32,false,true,ksplit>"};
   } else if (engine) {
     f->kern[0] = {(const void*)umma::flow_inverse_umma_kernel<32>, umma::Cfg<32>::kThreads, f->smem32, "ikf::umma::flow_inverse_umma_kernel<32,false,false>"};
     f->kern[1] = {(const void*)umma::flow_inverse_umma_kernel<64>, umma::Cfg<64>::kThreads, f->smem64, "ikf::umma::flow_inverse_umma_kernel<64,false,false>"};
     f->kern[2] = {(const void*)umma::flow_inverse_umma_kernel<128>, umma::Cfg<128>::kThreads, f->smem128, "ikf::umma::flow_inverse_umma_kernel<128,false,false>"};
     f->kern[3] = {(const void*)umma::flow_inverse_umma_kernel<32, true>, umma::Cfg<32, true>::kThreads, f->smem32j, "ikf::umma::flow_inverse_umma_kernel<32,true,false>"};
+    f->kern[4] = {(const void*)umma::flow_inverse_umma_kernel<32, false, false, true>, umma::Cfg<32, false, true>::kThreads, sizeof(umma::Smem<32, false, true>) + 1024, "ikf::umma::flow_inverse_umma_kernel<32,false,false,ksplit>"};
   } else {
     f->kern[0] = {(const void*)flow_inverse_kernel<32>, kThreads, f->smem32, "ikf::flow_inverse_kernel<32>"};
     f->kern[1] = {(const void*)flow_inverse_kernel<64>, kThreads, f->smem64, "ikf::flow_inverse_kernel<64>"};
   }
   if (!f->jit) f->kern[3] = IkfFlow::Kernel();
+  if (const char* env = std::getenv("IKFLOW_B200_KSPLIT")) f->ksplit = std::atoi(env) != 0;
+  if (!f->ksplit || KCH % 4 != 0 || NT > 16) f->kern[4] = IkfFlow::Kernel();  // (flag bits: 2 NT <= 32; whole chunk pairs per half)
   {
     // the teams spin on each other's flags, so every CTA of a launch must be resident: size the slot count from
     // what the device really fits
@@ -477,7 +485,7 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
     const int v = std::atoi(env);
     if (v == 1 || v == 2 || v == 4) f->cluster_pref = f->cluster_pref_jit = v;
   }
-  if (e == cudaSuccess && engine && std::max(f->cluster_pref, f->cluster_pref_jit) > 1) {
+  if (e == cudaSuccess && engine && (std::max(f->cluster_pref, f->cluster_pref_jit) > 1 || f->kern[4].fn)) {
     // how many clusters of cs CTAs the device holds at once (clusters are placed inside a GPC, so this is not num_sms / cs)
     for (IkfFlow::Kernel& k : f->kern) {
       if (!k.fn) continue;
@@ -497,6 +505,7 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
           n_clusters = 0;
         }
         k.max_slots_cs[cs] = (n_clusters * cs / NT) / cs * cs;  // whole groups of cs teams
+        if (&k == &f->kern[4] && cs == 2) f->ks_slots_max = n_clusters / NT;  // a k-split team = NT clusters of 2
       }
     }
   }
@@ -547,11 +556,25 @@ struct GatherArgs {
   int ld, row0;
 };
 
+static int flow_launch_locked(IkfFlow* flow, const float* in, int in_ld, const float* cond, int cond_ld, int cond_rows,
+                              int cond_cols, float* out, int out_ld, int out_cols, int batch, int block_first, int block_last,
+                              int finalize, int clamp, void* stream, const char* name, int forward, float* logdet_out,
+                              const GatherArgs* gather);
+
 static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* cond, int cond_ld, int cond_rows,
                        int cond_cols, float* out, int out_ld, int out_cols, int batch, int block_first, int block_last,
                        int finalize, int clamp, void* stream, const char* name, int forward = 0, float* logdet_out = nullptr,
                        const GatherArgs* gather = nullptr) {
   if (!flow) return fail(IKF_EINVAL, "%s: flow is NULL", name);
+  std::lock_guard<std::mutex> lock(flow->mu);  // see IkfFlow::mu
+  return flow_launch_locked(flow, in, in_ld, cond, cond_ld, cond_rows, cond_cols, out, out_ld, out_cols, batch, block_first, block_last,
+                            finalize, clamp, stream, name, forward, logdet_out, gather);
+}
+
+static int flow_launch_locked(IkfFlow* flow, const float* in, int in_ld, const float* cond, int cond_ld, int cond_rows,
+                              int cond_cols, float* out, int out_ld, int out_cols, int batch, int block_first, int block_last,
+                              int finalize, int clamp, void* stream, const char* name, int forward, float* logdet_out,
+                              const GatherArgs* gather) {
   if (batch < 0) return fail(IKF_EINVAL, "%s: negative batch %d", name, batch);
   if (batch == 0) return IKF_OK;
   const IkfFlowDesc& d = flow->desc;
@@ -565,7 +588,6 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
     return fail(IKF_EINVAL, "%s: bad block range [%d..%d] for %d blocks", name, block_first, block_last, d.nb_nodes);
   DeviceGuard guard(flow->device);
   if (!guard.ok) return fail(IKF_ECUDA, "%s: cudaSetDevice(%d) failed", name, flow->device);
-  std::lock_guard<std::mutex> lock(flow->mu);
   // A previous launch that gave up on an inter-CTA wait has written into the mapped status word by now (or will have
   // by the time its stream is synchronised): refuse to build on its garbage.  No synchronisation: a plain host read.
   if (flow->status_host[0] & (IKF_STATUS_SYNC_TIMEOUT | IKF_STATUS_RANGE)) {
@@ -594,19 +616,28 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   if (flow->forced_rt) rt = flow->forced_rt;
   p.n_rowgroups = (batch + rt - 1) / rt;
   p.slots = std::min(p.n_rowgroups, flow->slots_max);
-  const IkfFlow::Kernel& k = flow->kern[(rt == 32 && flow->jit) ? 3 : rt == 32 ? 0 : rt == 64 ? 1 : 2];
+  // k-split pairs (Cfg::KS): 64-row groups, two CTAs per feature tile; for every batch that fits one wave of such teams
+  const bool ks = flow->engine && flow->kern[4].fn && flow->cluster_ok && !flow->forced_rt && (batch + 63) / 64 <= flow->ks_slots_max;
+  if (ks) {
+    rt = 64;
+    p.n_rowgroups = (batch + 63) / 64;
+    p.slots = p.n_rowgroups;
+  }
+  const IkfFlow::Kernel& k = flow->kern[ks ? 4 : (rt == 32 && flow->jit) ? 3 : rt == 32 ? 0 : rt == 64 ? 1 : 2];
   // Clusters of cs CTAs = the CTAs with the same feature tile of cs neighbouring teams share every weight chunk by
   // multicast (FlowParams::cluster).  Needs cs teams at least; the slot count becomes a multiple of cs (surplus teams
   // walk empty row groups).
   int cs = 1;
-  if (flow->engine && flow->cluster_ok)
+  if (ks) cs = 2;  // (the pair is the cluster; no weight multicast: its CTAs multiply different k-chunks)
+  else if (flow->engine && flow->cluster_ok)
     for (int c = (&k == &flow->kern[3]) ? flow->cluster_pref_jit : flow->cluster_pref; c > 1; c >>= 1)
       if (p.n_rowgroups >= c && k.max_slots_cs[c] >= c) {
         cs = c;
         break;
       }
-  if (cs > 1) p.slots = std::min((p.n_rowgroups + cs - 1) / cs * cs, k.max_slots_cs[cs]);
+  if (cs > 1 && !ks) p.slots = std::min((p.n_rowgroups + cs - 1) / cs * cs, k.max_slots_cs[cs]);
   p.cluster = cs;
+  p.ksplit = ks ? 1 : 0;
   p.n_peers = 0;
   if (gather) {
     p.n_peers = flow->n_ranks;
@@ -618,7 +649,7 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
       p.peer_flag[r] = flow->peer_flag[r];
     }
     p.peer_seq = ++flow->peer_seq;
-    flow->peer_count_total += (uint32_t)p.slots;  // one writer CTA (t = 0) per team slot
+    flow->peer_count_total += (uint32_t)p.slots * (ks ? 2u : 1u);  // the writer CTAs: t = 0 of every team slot (k-split: both halves)
     p.peer_count_target = flow->peer_count_total;
   }
   p.epoch = flow->epoch;
@@ -629,7 +660,7 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
   const uint32_t rg_per_slot = (uint32_t)((p.n_rowgroups + p.slots - 1) / p.slots);
   flow->epoch += rg_per_slot * 2u * (uint32_t)(block_first - block_last + 1) * (uint32_t)(flow->n_big + 1) + 2u;
 
-  const int grid = p.slots * flow->NT;
+  const int grid = p.slots * flow->NT * (ks ? 2 : 1);
   flow->last_grid = grid;
   flow->last_cluster = cs;
   void* args[] = {(void*)&p};
@@ -669,6 +700,16 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
       flow->cluster_ok = false;
       last_error_ref() = std::string("cluster launch refused (") + cudaGetErrorString(e) + "), clusters disabled for this handle";
       p.cluster = 1;
+      if (ks) {  // no clusters, no k-split pairs: start over with the plain kernels
+        flow->kern[4] = IkfFlow::Kernel();
+        if (gather) {
+          flow->peer_count_total -= (uint32_t)p.slots * 2u;
+          --flow->peer_seq;
+        }
+        flow->epoch = p.epoch;
+        return flow_launch_locked(flow, in, in_ld, cond, cond_ld, cond_rows, cond_cols, out, out_ld, out_cols, batch, block_first,
+                                  block_last, finalize, clamp, stream, name, forward, logdet_out, gather);
+      }
       if (gather) flow->peer_count_total -= (uint32_t)p.slots;
       p.slots = std::min(p.n_rowgroups, flow->slots_max);
       if (gather) {

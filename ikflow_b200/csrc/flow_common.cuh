@@ -76,6 +76,9 @@ struct FlowParams {
   // chunk and multicasts it to all of them (one L2 read instead of `cluster`).  CTA -> (team slot, feature tile t):
   //   c = blockIdx.x / cluster, r = blockIdx.x % cluster (= %cluster_ctarank), t = c % NT, slot = (c / NT) * cluster + r
   int cluster;
+  // k-split pairs (flow_umma.cuh, Cfg::KS): cluster = 2, r = the CTA's half kh of the k-chunks and of the rows,
+  // slot = c / NT
+  int ksplit;
   // Fused gather of the batch-sharded solve (tcgen05 engine; n_peers = 0: off).  The ranks of one node each solve a
   // contiguous block of rows; instead of a collective after the kernel, the final epilogue stores its rows straight into
   // the gathered buffer of EVERY rank (peer-mapped pointers: NVLink stores), and the last CTA to finish raises this
@@ -271,17 +274,18 @@ __device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t expecte
   }
 }
 
-__device__ __forceinline__ void cta_coords(const FlowParams& p, int& slot, int& t) {
+__device__ __forceinline__ void cta_coords(const FlowParams& p, int& slot, int& t, int& kh) {
   const int cs = p.cluster > 1 ? p.cluster : 1;
   const int c = blockIdx.x / cs, r = blockIdx.x % cs;
   t = c % p.NT;
-  slot = (c / p.NT) * cs + r;
+  slot = p.ksplit ? c / p.NT : (c / p.NT) * cs + r;
+  kh = p.ksplit ? r : 0;
 }
 // index of this CTA inside team 0 (the team the debug trace follows), or -1
 __device__ __forceinline__ int trace_cta(const FlowParams& p) {
-  int slot, t;
-  cta_coords(p, slot, t);
-  return slot == 0 ? t : -1;
+  int slot, t, kh;
+  cta_coords(p, slot, t, kh);
+  return (slot == 0 && kh == 0) ? t : -1;
 }
 
 constexpr int kTraceEvents = 96;  // stamps per (CTA, layer): 0-15 phase events; per k-chunk i: 16+i landed (MMA warp), 32+i stage free

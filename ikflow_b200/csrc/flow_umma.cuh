@@ -98,10 +98,17 @@ __device__ __forceinline__ uint32_t split_one(float v) {
   }
 }
 
-template <int RT, bool JIT = false>
+// KS ("k-split"): a ROW GROUP OF 64 is shared by TWO CTAs per feature tile, a cluster of 2.  CTA (t, kh) multiplies only
+// the k-chunks of its half kh of every hidden layer (8 of 16: half the weight bytes through its shared memory, which is
+// what paces the hidden layers) against all 64 rows, hands the partial sums of the other CTA's 32 rows over through
+// distributed shared memory and finishes its own 32 rows: first layer, epilogue, publication, last layer, coupling and
+// flow state are those of a 32-row CTA (RT = 32), at row offset 32 kh inside the team's 64-row exchange tiles.
+template <int RT, bool JIT = false, bool KS = false>
 struct Cfg {
   static_assert(!JIT || RT == 32, "the just-in-time first layer is written for 32-row groups");
-  static constexpr int kAPlane = RT * kKC * 2;       // one bf16 plane of an activation k-chunk [RT][64]
+  static_assert(!KS || (RT == 32 && !JIT), "k-split pairs: 32 rows per CTA, exchanged first layer");
+  static constexpr int kXRows = KS ? 2 * RT : RT;     // rows of the exchanged activation tiles = rows of the MMA
+  static constexpr int kAPlane = kXRows * kKC * 2;    // one bf16 plane of an activation k-chunk [rows][64]
   static constexpr int kAChunk = 2 * kAPlane;        // head + tail
   static constexpr int kW1Off = kWChunkU + kAChunk;   // JIT: first-layer weights of the chunk's 64 features
   static constexpr int kStage = JIT ? ((kW1Off + kJitChunkBytes + 1023) / 1024) * 1024 : kW1Off;  // 40 KB (RT=32; JIT 45 KB) / 48 KB (RT=64)
@@ -124,8 +131,9 @@ struct Cfg {
   // which is idle while it is needed (nothing is exchanged between the end of a subnet's second hidden layer and the
   // publication of the next subnet's first layer).
   static constexpr bool kSplit = !JIT;
-  static constexpr int kWStages = RT == 128 ? 3 : 4;
-  static constexpr int kAStages = RT == 128 ? 2 : (RT == 64 ? 3 : 4);
+  static constexpr int kWStages = (RT == 128 || KS) ? 3 : 4;
+  static constexpr int kAStages = RT == 128 ? 2 : ((RT == 64 || KS) ? 3 : 4);
+  static constexpr int kRecvBytes = KS ? RT * kFTU * 4 : 16;  // k-split: the peer's partial sums of this CTA's rows [32][128] fp32
   // loader warp w owns the ring stages s with s % kLoaders == w: its waits on a stage's barriers are then strictly in
   // order (a waiter may lag an mbarrier by at most one phase)
   // JIT: two loader warps (each owns two stages), so that the CTA stays at 11 warps: with 13 the register file grants
@@ -151,7 +159,7 @@ struct Cfg {
   static constexpr int kGenThreads = 32 * kGenWarps;
   static constexpr int kThreads = (kMmaWarp + kMmaWarps + kHelpers) * 32;
   static constexpr int kVtBytes = 32 * kFTU * 4;         // fp32 [32 rows][128 features] of one group: last-layer operand
-  static constexpr int kAccCols = 2 * RT;  // one accumulator tile: D[:, 0:2RT] (N-stacked products)
+  static constexpr int kAccCols = 2 * kXRows;  // one accumulator tile: D[:, 0:2 rows] (N-stacked products)
   static constexpr int kTmemCols = kMmaWarps * kAccCols <= 32 ? 32 : (kMmaWarps * kAccCols <= 64 ? 64 : (kMmaWarps * kAccCols <= 128 ? 128 : (kMmaWarps * kAccCols <= 256 ? 256 : 512)));
   static_assert(kMmaWarps * kAccCols <= 512, "TMEM has 512 columns");
   static_assert(kStage % 1024 == 0, "stages must keep the 1024-byte alignment of the swizzle atoms");
@@ -159,9 +167,9 @@ struct Cfg {
   static_assert(JIT || kGroups * kVtBytes <= kAStages * kAChunk, "the last layer's scratch must fit the activation ring");
 };
 
-template <int RT, bool JIT = false>
+template <int RT, bool JIT = false, bool KS = false>
 struct __align__(1024) Smem {
-  using C = Cfg<RT, JIT>;
+  using C = Cfg<RT, JIT, KS>;
   // JIT kernel: unified ring [weights head|tail][activations head|tail][first-layer weights]; the others: split rings
   uint8_t ring[JIT ? C::kStages : 1][JIT ? C::kStage : 1024];
   uint8_t wring[JIT ? 1 : C::kWStages][JIT ? 1024 : kWChunkU];   // [head | tail] x [128 features][64 k]
@@ -169,6 +177,7 @@ struct __align__(1024) Smem {
   // per epilogue group: fp32 activations [32 rows][128 features] for the last layer (float4 slots swizzled); the kernels
   // with split rings keep it in `aring` instead
   uint8_t vt[JIT ? C::kGroups : 1][JIT ? C::kVtBytes : 1024];
+  uint8_t recv[C::kRecvBytes];  // k-split: written by the peer CTA of the cluster (st.shared::cluster), [32 rows][128 features] fp32
   float small[2][C::kSmFloats];
   float u[RT][kPad];  // flow state
   float cnd[RT][8];
@@ -181,6 +190,7 @@ struct __align__(1024) Smem {
   uint64_t w1empty[C::kStages];  // JIT: ... and have been used (the stage's weight/activation areas may still be busy)
   uint64_t small_full[2], small_empty[2];
   uint64_t dfull, dempty;
+  uint64_t rbar;  // k-split: "the peer's partial sums have arrived" (128 remote arrivals per hidden layer)
   uint32_t tmem_base;
 };
 
@@ -439,9 +449,10 @@ __device__ __forceinline__ void first_layer_tile(uint32_t w_a, uint32_t b_a, con
   if (F16 && vmax > 65504.f) report_range(status, status_host);
 }
 
-template <int RT, bool JIT = false, bool F16 = false>
-__global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_kernel(const FlowParams p) {
-  using C = Cfg<RT, JIT>;
+template <int RT, bool JIT = false, bool F16 = false, bool KS = false>
+__global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_umma_kernel(const FlowParams p) {
+  using C = Cfg<RT, JIT, KS>;
+  constexpr int XR = C::kXRows;  // rows of a row group (of the exchanged tiles, of the MMAs); RT = rows this CTA finishes
   constexpr int kStages = C::kStages;
   constexpr int G = C::kGroups, ER = C::kEpiRows, ET = C::kEpiThreads;
   // Accumulator tiles per hidden layer: k-chunk i goes to tile i % kAcc, the epilogue adds the tiles in a fixed order.
@@ -450,19 +461,22 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
   // with one tile.  bf16x3 does not notice (its 16-bit operands dominate its error); fp16x3, whose operands carry 22 bits,
   // is limited by exactly this, so it spreads the chunks over 4 tiles (2 at 128 rows: TMEM has 512 columns) and sums
   // them in fp32 round-to-nearest.
-  constexpr int kAcc = F16 ? (RT == 128 ? 2 : 4) : 1;
+  constexpr int kAcc = F16 ? (XR == 128 ? 2 : 4) : 1;
   constexpr int kTmemColsK = kAcc * C::kAccCols <= 32 ? 32 : (kAcc * C::kAccCols <= 64 ? 64 : (kAcc * C::kAccCols <= 128 ? 128 : (kAcc * C::kAccCols <= 256 ? 256 : 512)));
   static_assert(kAcc * C::kAccCols <= 512 && C::kMmaWarps == 1, "TMEM has 512 columns; the tiles are dealt by chunk index");
   extern __shared__ uint8_t smem_raw[];
-  Smem<RT, JIT>& sm = *reinterpret_cast<Smem<RT, JIT>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Smem<RT, JIT, KS>& sm = *reinterpret_cast<Smem<RT, JIT, KS>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int NT = p.NT;            // hidden / 128
   const int KCH = p.H / kKC;      // 64-wide k-chunks per hidden layer (2 per producer)
-  int slot, t;
-  cta_coords(p, slot, t);
+  int slot, t, kh;                // k-split: kh = this CTA's half of the k-chunks = its half of the row group's rows
+  cta_coords(p, slot, t, kh);
+  const int KCHL = KS ? KCH / 2 : KCH;  // k-chunks this CTA multiplies per hidden layer
+  const int xrow0 = KS ? RT * kh : 0;   // this CTA's rows inside the row group / the exchanged tiles
+  const int FW = KS ? 2 : 1;            // publication flags per feature tile
   // CTAs per cluster: same t, neighbouring teams (FlowParams::cluster).  Read from the parameter bank where needed
   // (the kernel is at its register limit: no function-scope copies).
 #define IKF_CS (p.cluster > 1 ? p.cluster : 1)
@@ -477,7 +491,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
     }
     for (int s = 0; s < C::kWStages; ++s) {
       mbar_init(&sm.wfull[s], 1);
-      mbar_init(&sm.wempty[s], IKF_CS);
+      mbar_init(&sm.wempty[s], KS ? 1 : IKF_CS);  // (a k-split pair is a cluster too, but its CTAs load different chunks)
     }
     for (int s = 0; s < C::kAStages; ++s) {
       mbar_init(&sm.afull[s], 1);
@@ -489,6 +503,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
     }
     mbar_init(&sm.dfull, C::kMmaWarps);
     mbar_init(&sm.dempty, C::kEpiWarps);
+    mbar_init(&sm.rbar, C::kEpiThreads);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
@@ -506,7 +521,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
 
   uint8_t* act_slot = p.act + (size_t)slot * 2 * NT * kAStrideU;
   uint8_t* part_slot = reinterpret_cast<uint8_t*>(p.partial) + (size_t)slot * 2 * NT * kRTMaxU * kPartRowBytes;
-  uint32_t* aflag = p.act_flag + (size_t)slot * 2 * NT;
+  uint32_t* aflag = p.act_flag + (size_t)slot * 2 * NT * FW;  // [2 buffers][NT tiles][FW]
 
   const int n_blocks = p.block_first - p.block_last + 1;
   const int steps_per_rg = 2 * n_blocks;
@@ -623,15 +638,17 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
           for (int l = 0; l < p.n_big; ++l) {
             const uint8_t* wbase =
                 reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n * p.n_big + l) * NT + t) * KCH * kWChunkU;
-            for (int i = 0; i < KCH; ++i, ++pos) {
+            for (int i = 0; i < KCHL; ++i, ++pos) {
               const int st = pos % C::kWStages;
               const uint32_t use = pos / C::kWStages;
-              const int kc = (2 * t + i) % KCH;
+              // fixed consumption order (the accumulation order never depends on timing), starting at the CTA's own chunks;
+              // k-split: inside this CTA's half of the layer
+              const int kc = KS ? KCHL * kh + (2 * t + i) % KCHL : (2 * t + i) % KCH;
               if (use > 0) mbar_wait_relaxed(&sm.wempty[st], (use - 1) & 1);  // clusters: free in EVERY CTA of the cluster
               if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 32 + i);
               if (lane == st) {
                 mbar_arrive_expect_tx(&sm.wfull[st], kWChunkU);
-                if (p.cluster > 1) {  // this CTA's share of the chunk, delivered to all CTAs of the cluster
+                if (!KS && p.cluster > 1) {  // this CTA's share of the chunk, delivered to all CTAs of the cluster
                   const uint32_t share = (uint32_t)kWChunkU / (uint32_t)p.cluster;
                   const uint32_t off = (blockIdx.x % (uint32_t)p.cluster) * share;
                   bulk_g2s_multicast(sm.wring[st] + off, wbase + (size_t)kc * kWChunkU + off, share, &sm.wfull[st], (uint16_t)((1u << p.cluster) - 1u));
@@ -661,22 +678,23 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
             const int buf = xchg & 1;
             const uint32_t expected = p.epoch + 1 + act_w[buf];
             const uint8_t* abase = act_slot + (size_t)buf * NT * kAStrideU;
-            const uint32_t* my_flag = aflag + buf * NT + (lane < NT ? lane : 0);
-            uint32_t ready = gave_up ? 0xffffffffu : 0u;  // bit c: producer c has published (warp-uniform)
-            for (int i = 0; i < KCH; ++i, ++pos) {
+            const uint32_t* my_flag = aflag + buf * NT * FW + (lane < NT * FW ? lane : 0);
+            uint32_t ready = gave_up ? 0xffffffffu : 0u;  // bit: that producer CTA has published (warp-uniform); k-split: two per tile
+            for (int i = 0; i < KCHL; ++i, ++pos) {
               const int st = pos % C::kAStages;
               const uint32_t use = pos / C::kAStages;
-              const int kc = (2 * t + i) % KCH;
+              const int kc = KS ? KCHL * kh + (2 * t + i) % KCHL : (2 * t + i) % KCH;
               const int c = kc >> 1;
+              const uint32_t need = KS ? (3u << (2 * c)) : (1u << c);  // k-split: both halves of the producer tile's rows
               if (use > 0) mbar_wait_relaxed(&sm.aempty[st], (use - 1) & 1);
               if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 64 + i);
               uint32_t spins = 0;
               long long t0 = 0;
-              while (!((ready >> c) & 1u)) {
+              while ((ready & need) != need) {
                 bool ok = false;
-                if (lane < NT && !((ready >> lane) & 1u)) ok = (int32_t)(ld_relaxed(my_flag) - expected) >= 0;
+                if (lane < NT * FW && !((ready >> lane) & 1u)) ok = (int32_t)(ld_relaxed(my_flag) - expected) >= 0;
                 ready |= __ballot_sync(0xffffffffu, ok);
-                if ((ready >> c) & 1u) break;
+                if ((ready & need) == need) break;
                 ++spins;
                 if (spins == 64) t0 = clock64();
                 if (spins > 64) {
@@ -854,8 +872,8 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
     // loop ("once per active thread"); behind elect.sync the UTCHMMAs are emitted back to back: 840 -> 560 cycles per
     // k-chunk for the issuing thread (scripts/ubench/umma_loop.cu), which is what paces the hidden layers. =====
     {
-      constexpr uint32_t idesc = make_idesc(kFTU, RT, F16);       // N = RT
-      constexpr uint32_t idesc2 = make_idesc(kFTU, 2 * RT, F16);  // N = 2 RT: activation head and tail stacked
+      constexpr uint32_t idesc = make_idesc(kFTU, XR, F16);       // N = rows of the row group
+      constexpr uint32_t idesc2 = make_idesc(kFTU, 2 * XR, F16);  // N = 2 x rows: activation head and tail stacked
       uint32_t ring_pos = 0;
       uint32_t layers = 0;  // hidden layers issued so far
       const bool x3 = p.precision != IKF_PRECISION_BF16X1;
@@ -863,7 +881,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
       const uint64_t d_a0 = make_desc(smem_u32(sm.ring[0]) + kWChunkU);
       const int mw = warp - C::kMmaWarp;  // this warp's chunks: i = mw (mod kMmaWarps), its accumulator tile: mw
       const uint32_t tmem_u0 = __shfl_sync(0xffffffffu, tmem, 0);
-      constexpr uint32_t kCorrOff = F16 ? RT : 0;  // fp16x3: the scaled correction terms have their own accumulator
+      constexpr uint32_t kCorrOff = F16 ? XR : 0;  // fp16x3: the scaled correction terms have their own accumulator
       for (int g = 0; g < total_steps; ++g) {
         for (int l = 0; l < p.n_big; ++l) {
           if (layers > 0) mbar_wait(&sm.dempty, (layers - 1) & 1);  // the epilogue has drained the accumulators
@@ -872,7 +890,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
             // split rings: chunk number ring_pos + i sits in weight stage (ring_pos + i) % kWStages and activation stage
             // (ring_pos + i) % kAStages
             const uint64_t d_w0 = make_desc(smem_u32(&sm.wring[0][0])), d_as0 = make_desc(smem_u32(&sm.aring[0][0]));
-            for (int i = mw; i < KCH; i += C::kMmaWarps) {
+            for (int i = mw; i < KCHL; i += C::kMmaWarps) {
               const uint32_t pos = ring_pos + (uint32_t)i;
               const int sw = pos % C::kWStages, sa = pos % C::kAStages;
               mbar_wait(&sm.wfull[sw], (pos / C::kWStages) & 1);
@@ -887,12 +905,12 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
                 else
                   mma_chunk_x1(tmem_u, idesc, dwh, da, i >= kAcc);
                 // both stages are free once these MMAs have read them (clusters: the weight stage is refilled by every CTA)
-                if (p.cluster > 1) mma_commit_multicast(&sm.wempty[sw], (uint16_t)((1u << p.cluster) - 1u)); else mma_commit(&sm.wempty[sw]);
+                if (!KS && p.cluster > 1) mma_commit_multicast(&sm.wempty[sw], (uint16_t)((1u << p.cluster) - 1u)); else mma_commit(&sm.wempty[sw]);
                 mma_commit(&sm.aempty[sa]);
               }
               __syncwarp();
             }
-            ring_pos += KCH;
+            ring_pos += KCHL;
           } else {
             // unified ring (just-in-time kernel; every layer starts at stage 0): stage index = i % kStages is a compile-time
             // constant inside the unrolled group, so the 3 descriptors of every stage stay in uniform registers (428 instead
@@ -946,7 +964,13 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
     const uint32_t vt_a = JIT ? smem_u32(sm.vt[h]) : smem_u32(&sm.aring[0][0]) + h * C::kVtBytes;
     const int j8 = lane & 7;     // publish: row inside an 8-row block after the lane transpose
     const uint32_t xin_a = smem_u32(&sm.a[0][0]);
-    const bool tiled_first = !JIT && !(p.debug & 4096);
+    const bool tiled_first = !JIT && (KS || !(p.debug & 4096));
+    // k-split: shared::cluster addresses of the peer CTA's receive buffer and barrier
+    uint32_t peer_recv = 0, peer_rbar = 0;
+    if constexpr (KS) {
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_recv) : "r"(smem_u32(sm.recv)), "r"((uint32_t)(kh ^ 1)));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_rbar) : "r"(smem_u32(&sm.rbar)), "r"((uint32_t)(kh ^ 1)));
+    }
 
     // u <- u[:, table]
     auto permute_state = [&](const int* table) {
@@ -971,7 +995,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
       const int rg = slot + rgi * p.slots;  // >= n_rowgroups: an empty row group of a cluster in lock step
       for (int i = tid; i < RT * kPad; i += ET) {
         const int r = i / kPad, j = i % kPad;
-        const int row = rg * RT + r;
+        const int row = rg * XR + xrow0 + r;
         float uv = 0.f, cv = 0.f;
         if (row < p.batch) {
           if (j < p.W) uv = p.in[(size_t)row * p.in_ld + j];
@@ -1037,6 +1061,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
             const int tile0 = warp * kTilesPerWarp;
             const int rb = tile0 / (kFTU / 16), fb0 = tile0 % (kFTU / 16);
             uint8_t* dst0 = act_slot + ((size_t)(axchg & 1) * NT + t) * kAStrideU;
+            const int rb_out = KS ? kh : rb;  // 32-row block inside the exchanged tile (k-split: this CTA's half of the rows)
             auto run = [&](auto kb) {
               constexpr int KB = decltype(kb)::value;
               float x[4][KB];
@@ -1049,7 +1074,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
                 }
 #pragma unroll
               for (int ti = 0; ti < kTilesPerWarp; ++ti)
-                first_layer_tile<KB, C::kAPlane, F16>(sp_a + (kSmFirstW - C::kSmShift) * 4, sp_a + (kSmFirstB - C::kSmShift) * 4, x, rb, fb0 + ti,
+                first_layer_tile<KB, C::kAPlane, F16>(sp_a + (kSmFirstW - C::kSmShift) * 4, sp_a + (kSmFirstB - C::kSmShift) * 4, x, rb_out, fb0 + ti,
                                                  lane, dst0, C::kAChunk, p.status, p.status_host);
             };
             if (kin <= 12) run(std::integral_constant<int, 12>{});
@@ -1089,6 +1114,38 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
               mbar_wait(&sm.dfull, layers & 1);
               tc_fence_after();
               if (tid == 0) trace_ev(p, g * 4 + l - 1, 7);
+              if constexpr (KS) {
+                // ---- k-split: this CTA's tiles hold the partial sums (its half of k) of ALL 64 rows.  The other CTA's 32
+                //      rows go to its receive buffer through distributed shared memory ([row][feature]: a warp stores 128
+                //      contiguous bytes), the own 32 rows stay in registers and get the peer's half added ----
+                float other[RT];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {  // hh = 0: the peer's rows, 1: the own rows
+                  const int c0 = hh == 0 ? RT * (kh ^ 1) : RT * kh;
+#pragma unroll
+                  for (int m = 0; m < kAcc; ++m) {
+                    if (m >= KCHL) break;
+                    float tmp[32], tmp2[32];
+                    tmem_ld32(taddr + m * C::kAccCols + c0, tmp);
+                    if (x3) {
+                      tmem_ld32(taddr + m * C::kAccCols + XR + c0, tmp2);
+#pragma unroll
+                      for (int r = 0; r < 32; ++r) tmp[r] = F16 ? fmaf(tmp2[r], 1.f / kTailScaleF16, tmp[r]) : tmp[r] + tmp2[r];
+                    }
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                      if (hh == 0) other[r] = m == 0 ? tmp[r] : other[r] + tmp[r];
+                      else v[r] = m == 0 ? tmp[r] : v[r] + tmp[r];
+                    }
+                  }
+                  if (hh == 0) {
+#pragma unroll
+                    for (int r = 0; r < RT; ++r)
+                      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(peer_recv + (uint32_t)((r * kFTU + f) * 4)), "f"(other[r]) : "memory");
+                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_rbar) : "memory");
+                  }
+                }
+              } else {
 #pragma unroll
               for (int c0 = 0; c0 < ER; c0 += 32) {
                 // the accumulator tiles (k-chunks i = m mod kAcc), added in a fixed order
@@ -1106,9 +1163,26 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
                   for (int r = 0; r < 32; ++r) v[c0 + r] = m == 0 ? tmp[r] : v[c0 + r] + tmp[r];
                 }
               }
+              }
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&sm.dempty);
+              if constexpr (KS) {
+                // the peer's partial sums of my rows (one barrier phase per hidden layer, in lock step: neither CTA can run a
+                // layer ahead, it needs the other's publication first)
+                {
+                  uint32_t ok = 0;
+                  const long long tw = clock64();
+                  while (!ok) {
+                    asm volatile("{\n\t.reg .pred pp;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 pp, [%1], %2;\n\tselp.u32 %0, 1, 0, pp;\n\t}"
+                                 : "=r"(ok) : "r"(smem_u32(&sm.rbar)), "r"(layers & 1u) : "memory");
+                    if (!ok && clock64() - tw > 4000000000LL) __trap();
+                  }
+                }
+                const uint32_t rv = smem_u32(sm.recv) + (uint32_t)(f * 4);
+#pragma unroll
+                for (int r = 0; r < RT; ++r) v[r] += lds32(rv + (uint32_t)(r * kFTU * 4));
+              }
               ++layers;
               const float bb = lds32(sp_a + (kSmBigB - C::kSmShift + (l - 1) * kFTU + f) * 4);
 #pragma unroll
@@ -1146,7 +1220,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
                     }
                   }
                 }
-                const uint32_t off = tile_off_bytes(row0 + r0 + j8, kf8);
+                const uint32_t off = tile_off_bytes(xrow0 + row0 + r0 + j8, kf8);
                 stg128(dst + off, __byte_perm(wd[0], wd[1], 0x5410), __byte_perm(wd[2], wd[3], 0x5410),
                        __byte_perm(wd[4], wd[5], 0x5410), __byte_perm(wd[6], wd[7], 0x5410));
                 stg128(dst + C::kAPlane + off, __byte_perm(wd[0], wd[1], 0x7632), __byte_perm(wd[2], wd[3], 0x7632),
@@ -1172,7 +1246,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
               // flag store lets consumers read stale chunks (scripts/stress_flow.py); its MEMBAR.GPU costs ~1 us.
               if (tid == 0) {
                 trace_ev(p, g * 4 + l, 4);
-                st_release(aflag + buf * NT + t, p.epoch + 1 + act_w[buf]);
+                st_release(aflag + (buf * NT + t) * FW + (KS ? kh : 0), p.epoch + 1 + act_w[buf]);
                 trace_ev(p, g * 4 + l, 5);
               }
               ++act_w[buf];
@@ -1247,7 +1321,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
                 for (int q = 0; q < 2; ++q) {
                   const float v0 = kq == 0 ? po[q][0] : kq == 1 ? po[q][2] : kq == 2 ? po[q][4] : po[q][6];
                   const float v1 = kq == 0 ? po[q][1] : kq == 1 ? po[q][3] : kq == 2 ? po[q][5] : po[q][7];
-                  st_ll(part_slot + (((size_t)pb * NT + t) * RT + row0 + ps * 32 + 2 * rp + q) * kPartRowBytes + (og * 4 + kq) * 16,
+                  st_ll(part_slot + (((size_t)pb * NT + t) * XR + xrow0 + row0 + ps * 32 + 2 * rp + q) * kPartRowBytes + (og * 4 + kq) * 16,
                         v0, v1, pexp);
                 }
               }
@@ -1262,7 +1336,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
           for (int i = tid; i < RT * 4; i += ET) {
             const int r = i >> 2, o4 = i & 3;
             float4 acc = lds128(sp_a + (kSmLastB - C::kSmShift + 4 * o4) * 4);
-            const uint8_t* src = part_slot + ((size_t)pb * NT * RT + r) * kPartRowBytes + (2 * o4) * 16;
+            const uint8_t* src = part_slot + ((size_t)pb * NT * XR + xrow0 + r) * kPartRowBytes + (2 * o4) * 16;
             const bool need0 = 2 * o4 < n_units, need1 = 2 * o4 + 1 < n_units;
             for (int c0 = 0; c0 < NT; c0 += 8) {
               uint4 x0[8], x1[8];
@@ -1275,8 +1349,8 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
                   x0[c] = make_uint4(0u, pexp, 0u, pexp);
                   x1[c] = make_uint4(0u, pexp, 0u, pexp);
                   if (c0 + c < NT) {
-                    if (need0) x0[c] = ld_ll(src + (size_t)(c0 + c) * RT * kPartRowBytes);
-                    if (need1) x1[c] = ld_ll(src + (size_t)(c0 + c) * RT * kPartRowBytes + 16);
+                    if (need0) x0[c] = ld_ll(src + (size_t)(c0 + c) * XR * kPartRowBytes);
+                    if (need1) x1[c] = ld_ll(src + (size_t)(c0 + c) * XR * kPartRowBytes + 16);
                   }
                 }
 #pragma unroll
@@ -1334,7 +1408,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
       if (t == 0) {
         for (int i = tid; i < RT * p.out_cols; i += ET) {
           const int r = i / p.out_cols, j = i % p.out_cols;
-          const int row = rg * RT + r;
+          const int row = rg * XR + xrow0 + r;
           if (row >= p.batch) continue;
           float o;
           if (p.finalize) {
@@ -1353,7 +1427,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT>::kThreads, 1) flow_inverse_umma_k
         }
         if (p.forward && p.logdet_out != nullptr)
           for (int r = tid; r < RT; r += ET)
-            if (rg * RT + r < p.batch) p.logdet_out[rg * RT + r] = sm.logdet[r];
+            if (rg * XR + xrow0 + r < p.batch) p.logdet_out[rg * XR + xrow0 + r] = sm.logdet[r];
       }
       bar_epi<ET>();
     }

@@ -264,6 +264,7 @@ def test_jit_first_layer_is_bitwise_identical_to_the_exchanged_one(batch, monkey
     sd = make_synthetic_state_dict(hp, robot.actuated_joints_limits, seed=0)
     latent, poses, cond = _inputs(batch, 7)
     outs = []
+    monkeypatch.setenv("IKFLOW_B200_KSPLIT", "0")  # (batches this small would otherwise go to the k-split kernel)
     for jit in ("1", "0"):
         monkeypatch.setenv("IKFLOW_B200_JIT", jit)
         model = ikflow_b200.glow_cNF_model(hp, robot, 8, 7)
@@ -517,7 +518,7 @@ def test_nan_inputs_propagate_like_torch_clamp_and_are_reported():
 def test_last_kernel_reports_what_was_launched():
     solver, hp, sd = _solver(12, 7, 3, 1024)
     latent, poses, cond = _inputs(2048, 7)
-    for batch, tag in ((512, "<32,true,true>"), (1024, "<64,false,true>"), (2048, "<128,false,true>")):  # <rows, just-in-time first layer, fp16x3>
+    for batch, tag in ((512, "<32,false,true,ksplit>"), (1024, "<64,false,true>"), (2048, "<128,false,true>")):  # <rows per CTA, just-in-time first layer, fp16x3>
         solver.nn_model.inverse(latent[:batch].to(DEV), cond[:batch].to(DEV))
         assert solver.nn_model.last_kernel().endswith("flow_inverse_umma_kernel" + tag), solver.nn_model.last_kernel()
 
@@ -548,3 +549,51 @@ def test_weight_multicast_clusters_are_bitwise_identical_to_unclustered_launches
         assert model.last_cluster() == (int(cs) if n_groups >= int(cs) else (2 if cs == "4" and n_groups >= 2 else 1)), (model.last_cluster(), cs)
     assert torch.equal(outs[0], outs[1])
     assert (outs[0].cpu() - _oracle(sd, hp, latent, cond)).abs().max() < TOL
+
+
+# ---- k-split pairs (Cfg::KS): 64-row groups shared by two CTAs per feature tile, DSMEM reduction of the partial sums ----
+@pytest.mark.parametrize("precision", ["fp16x3", "bf16x3"])
+@pytest.mark.parametrize("batch", [1, 33, 64, 65, 300, 512, 576])
+def test_ksplit_kernel_matches_oracle(batch, precision, monkeypatch):
+    """The kernel of every batch up to 576 rows: each CTA multiplies half of the k-chunks of every hidden layer against the
+    64 rows of its team, hands the other CTA's 32 rows over through distributed shared memory and finishes its own 32."""
+    model, hp, sd = _model_with_precision(precision)
+    latent, poses, cond = _inputs(batch, 7)
+    out = model.inverse(latent.to(DEV), cond.to(DEV))
+    assert "ksplit" in model.last_kernel() and model.last_cluster() == 2, model.last_kernel()
+    assert (out.cpu() - _oracle(sd, hp, latent, cond)).abs().max() < (1.5e-5 if precision == "fp16x3" else TOL)
+    for _ in range(20):
+        assert torch.equal(model.inverse(latent.to(DEV), cond.to(DEV)), out)  # fixed accumulation / reduction order
+    assert model.status() == 0
+    monkeypatch.setenv("IKFLOW_B200_KSPLIT", "0")
+    plain, _, _ = _model_with_precision(precision)
+    ref = plain.inverse(latent.to(DEV), cond.to(DEV))
+    assert "ksplit" not in plain.last_kernel()
+    assert (ref - out).abs().max() < 2e-5  # same arithmetic, another summation order
+
+
+def test_ksplit_kernel_other_shapes_and_directions():
+    """fetch_arm geometry (width 10, first-layer K = 13, 16 blocks), the forward pass with its log-det, block ranges, a
+    single broadcast pose and repeat-major tiling -- all through the k-split kernel."""
+    solver, hp, sd = _solver(16, 10, 3, 1024, "fetch_arm")
+    latent = torch.randn(200, 10, generator=torch.Generator().manual_seed(1))
+    _, poses = jk.sample_joint_angles_and_poses(jk.FETCH_ARM, 200, seed=2)
+    cond = torch.cat([poses, torch.zeros(200, 1)], dim=1)
+    out = solver.nn_model.inverse(latent.to(DEV), cond.to(DEV))
+    assert "ksplit" in solver.nn_model.last_kernel()
+    assert (out.cpu() - _oracle(sd, hp, latent, cond)).abs().max() < TOL
+    x = (torch.rand(200, 10, generator=torch.Generator().manual_seed(3)) * 2 - 1) * 2.0
+    z, logdet = solver.nn_model(x.to(DEV), c=cond.to(DEV), rev=False)
+    assert "ksplit" in solver.nn_model.last_kernel()
+    z_ref, ld_ref = freia_flow.flow_forward(sd, x, cond, hp.nb_nodes, hp.coeff_fn_config, hp.rnvp_clamp)
+    assert (z.cpu() - z_ref).abs().max() < TOL * max(1.0, float(z_ref.abs().max())) and (logdet.cpu() - ld_ref).abs().max() < 1e-3
+    psolver, php, psd = _solver(12, 7, 3, 1024)
+    lat, pos, cnd = _inputs(96, 7)
+    _, _, inter = freia_flow.flow_inverse(psd, lat, cnd, 12, 3, 2.5, return_intermediates=True)
+    part = psolver.nn_model.inverse_blocks(lat.to(DEV), cnd.to(DEV), 11, 6)
+    assert (part.cpu() - inter[5]).abs().max() < TOL
+    one = psolver.nn_model.inverse(lat.to(DEV), pos[:1].to(DEV))
+    assert (one.cpu() - _oracle(psd, php, lat, cnd[:1].repeat(96, 1))).abs().max() < TOL
+    tiled = psolver.nn_model.inverse(lat.to(DEV), pos[:32].to(DEV))
+    assert (tiled.cpu() - _oracle(psd, php, lat, cnd[:32].repeat(3, 1))).abs().max() < TOL
+    assert psolver.nn_model.status() == 0 and solver.nn_model.status() == 0
