@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
   // with one tile.  bf16x3 does not notice (its 16-bit operands dominate its error); fp16x3, whose operands carry 22 bits,
   // is limited by exactly this, so it spreads the chunks over 4 tiles (2 at 128 rows: TMEM has 512 columns) and sums
   // them in fp32 round-to-nearest.
-  constexpr int kAcc = F16 ? (XR == 128 ? 2 : 4) : 1;
+  constexpr int kAcc = F16 ? ((XR == 128 || KS) ? 2 : 4) : 1;  // k-split: 8 chunks per layer and CTA -> 2 tiles give the same 16 steps per tile
   constexpr int kTmemColsK = kAcc * C::kAccCols <= 32 ? 32 : (kAcc * C::kAccCols <= 64 ? 64 : (kAcc * C::kAccCols <= 128 ? 128 : (kAcc * C::kAccCols <= 256 ? 256 : 512)));
   static_assert(kAcc * C::kAccCols <= 512 && C::kMmaWarps == 1, "TMEM has 512 columns; the tiles are dealt by chunk index");
   extern __shared__ uint8_t smem_raw[];

@@ -384,7 +384,7 @@ def test_fp16x3_mode_is_as_close_to_fp32_as_fp32_is_to_fp64(batch):
         out = model.inverse(latent.to(DEV), cond.to(DEV)).cpu()[idx]
         assert (out - ref).abs().max() < gate, (precision, (out - ref).abs().max())
         assert (out.double() - ref64).abs().max() < gate
-        assert model.last_kernel().endswith("true>" if precision == "fp16x3" else "false>") and model.status() == 0
+        assert model.last_kernel().split("<")[1].rstrip(">").split(",")[2] == ("true" if precision == "fp16x3" else "false") and model.status() == 0
         assert model.effective_precision() == precision
 
 
