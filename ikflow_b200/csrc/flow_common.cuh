@@ -285,7 +285,7 @@ __device__ __forceinline__ void cta_coords(const FlowParams& p, int& slot, int& 
 __device__ __forceinline__ int trace_cta(const FlowParams& p) {
   int slot, t, kh;
   cta_coords(p, slot, t, kh);
-  return (slot == 0 && kh == 0) ? t : -1;
+  return slot == 0 ? t + p.NT * kh : -1;  // (k-split: the second CTA of every pair follows the first NT)
 }
 
 constexpr int kTraceEvents = 96;  // stamps per (CTA, layer): 0-15 phase events; per k-chunk i: 16+i landed (MMA warp), 32+i stage free

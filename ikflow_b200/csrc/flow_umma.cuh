@@ -133,7 +133,7 @@ struct Cfg {
   static constexpr bool kSplit = !JIT;
   static constexpr int kWStages = (RT == 128 || KS) ? 3 : 4;
   static constexpr int kAStages = RT == 128 ? 2 : ((RT == 64 || KS) ? 3 : 4);
-  static constexpr int kRecvBytes = KS ? RT * kFTU * 4 : 16;  // k-split: the peer's partial sums of this CTA's rows [32][128] fp32
+  static constexpr int kRecvBytes = KS ? 2 * RT * kFTU * 4 : 16;  // k-split: the peer's partial sums of this CTA's rows, 2 x [32][128] fp32
   // loader warp w owns the ring stages s with s % kLoaders == w: its waits on a stage's barriers are then strictly in
   // order (a waiter may lag an mbarrier by at most one phase)
   // JIT: two loader warps (each owns two stages), so that the CTA stays at 11 warps: with 13 the register file grants
@@ -177,7 +177,7 @@ struct __align__(1024) Smem {
   // per epilogue group: fp32 activations [32 rows][128 features] for the last layer (float4 slots swizzled); the kernels
   // with split rings keep it in `aring` instead
   uint8_t vt[JIT ? C::kGroups : 1][JIT ? C::kVtBytes : 1024];
-  uint8_t recv[C::kRecvBytes];  // k-split: written by the peer CTA of the cluster (st.shared::cluster), [32 rows][128 features] fp32
+  uint8_t recv[C::kRecvBytes];  // k-split: written by the peer CTA of the cluster (st.async), 2 x [128 features][32 rows] fp32, 16-byte units swizzled
   float small[2][C::kSmFloats];
   float u[RT][kPad];  // flow state
   float cnd[RT][8];
@@ -190,7 +190,8 @@ struct __align__(1024) Smem {
   uint64_t w1empty[C::kStages];  // JIT: ... and have been used (the stage's weight/activation areas may still be busy)
   uint64_t small_full[2], small_empty[2];
   uint64_t dfull, dempty;
-  uint64_t rbar;  // k-split: "the peer's partial sums have arrived" (128 remote arrivals per hidden layer)
+  uint64_t rbar;   // k-split: "the peer's partial sums have arrived" (one phase per hidden layer, 32 KB of st.async bytes)
+  uint64_t dhalf;  // k-split: the accumulator tile of the first half of the chunks is complete
   uint32_t tmem_base;
 };
 
@@ -299,6 +300,45 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// two accumulator slices with ONE wait: the second load's latency hides behind the first's.  _issue / _finish: other
+// work (remote stores) can be put between the loads and the wait.
+__device__ __forceinline__ void tmem_ld32x2_issue(uint32_t taddr0, uint32_t taddr1, uint32_t (&r)[32], uint32_t (&q)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr0));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31}, [%32];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+        "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]),
+        "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]),
+        "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31])
+      : "r"(taddr1));
+}
+__device__ __forceinline__ void tmem_ld32x2_finish(const uint32_t (&r)[32], const uint32_t (&q)[32], float (&v)[32], float (&w)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  // (the values are consumed through volatile moves below the wait: nothing may be scheduled above it)
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    uint32_t a, b;
+    asm volatile("mov.b32 %0, %1;" : "=r"(a) : "r"(r[i]));
+    asm volatile("mov.b32 %0, %1;" : "=r"(b) : "r"(q[i]));
+    v[i] = __uint_as_float(a), w[i] = __uint_as_float(b);
+  }
+}
+__device__ __forceinline__ void tmem_ld32x2(uint32_t taddr0, uint32_t taddr1, float (&v)[32], float (&w)[32]) {
+  uint32_t r[32], q[32];
+  tmem_ld32x2_issue(taddr0, taddr1, r, q);
+  tmem_ld32x2_finish(r, q, v, w);
 }
 
 __device__ __forceinline__ void st_ll(void* p, float v0, float v1, uint32_t seq) {
@@ -461,7 +501,9 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
   // with one tile.  bf16x3 does not notice (its 16-bit operands dominate its error); fp16x3, whose operands carry 22 bits,
   // is limited by exactly this, so it spreads the chunks over 4 tiles (2 at 128 rows: TMEM has 512 columns) and sums
   // them in fp32 round-to-nearest.
-  constexpr int kAcc = F16 ? ((XR == 128 || KS) ? 2 : 4) : 1;  // k-split: 8 chunks per layer and CTA -> 2 tiles give the same 16 steps per tile
+  // k-split: always two tiles, the first and the second half of the CTA's chunks (the first half is handed over to the peer
+  // while the second is still being multiplied); 8 chunks per layer and CTA -> the same 16 steps per tile as above
+  constexpr int kAcc = KS ? 2 : (F16 ? (XR == 128 ? 2 : 4) : 1);
   constexpr int kTmemColsK = kAcc * C::kAccCols <= 32 ? 32 : (kAcc * C::kAccCols <= 64 ? 64 : (kAcc * C::kAccCols <= 128 ? 128 : (kAcc * C::kAccCols <= 256 ? 256 : 512)));
   static_assert(kAcc * C::kAccCols <= 512 && C::kMmaWarps == 1, "TMEM has 512 columns; the tiles are dealt by chunk index");
   extern __shared__ uint8_t smem_raw[];
@@ -503,7 +545,9 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
     }
     mbar_init(&sm.dfull, C::kMmaWarps);
     mbar_init(&sm.dempty, C::kEpiWarps);
-    mbar_init(&sm.rbar, C::kEpiThreads);
+    mbar_init(&sm.rbar, 1);
+    if (KS) mbar_arrive_expect_tx(&sm.rbar, C::kRecvBytes);  // first phase: two hand-overs of [32 rows][128 features] fp32
+    mbar_init(&sm.dhalf, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
@@ -899,11 +943,15 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
               if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 16 + i);
               const uint64_t dwh = d_w0 + (uint64_t)(sw * (kWChunkU >> 4)), da = d_as0 + (uint64_t)(sa * (C::kAChunk >> 4));
               if (elect_one()) {
-                const uint32_t tmem_u = tmem_u0 + (uint32_t)((i % kAcc) * C::kAccCols);  // accumulator tile of this chunk
+                // accumulator tile of this chunk (k-split: first / second half of the CTA's chunks)
+                const int tile = KS ? (i >= KCHL / 2 ? 1 : 0) : i % kAcc;
+                const bool accum = KS ? (i != 0 && i != KCHL / 2) : i >= kAcc;
+                const uint32_t tmem_u = tmem_u0 + (uint32_t)(tile * C::kAccCols);
                 if (x3)
-                  mma_chunk_x3(tmem_u, tmem_u + kCorrOff, idesc2, idesc, dwh, dwh + (uint64_t)(kWPlaneU >> 4), da, i >= kAcc);
+                  mma_chunk_x3(tmem_u, tmem_u + kCorrOff, idesc2, idesc, dwh, dwh + (uint64_t)(kWPlaneU >> 4), da, accum);
                 else
-                  mma_chunk_x1(tmem_u, idesc, dwh, da, i >= kAcc);
+                  mma_chunk_x1(tmem_u, idesc, dwh, da, accum);
+                if (KS && i == KCHL / 2 - 1) mma_commit(&sm.dhalf);  // the first tile is complete: its hand-over starts now
                 // both stages are free once these MMAs have read them (clusters: the weight stage is refilled by every CTA)
                 if (!KS && p.cluster > 1) mma_commit_multicast(&sm.wempty[sw], (uint16_t)((1u << p.cluster) - 1u)); else mma_commit(&sm.wempty[sw]);
                 mma_commit(&sm.aempty[sa]);
@@ -1111,41 +1159,54 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
             if (l > 0) {
               // ---- hidden layer l-1: drain the accumulator ----
               if (tid == 0) trace_ev(p, g * 4 + l - 1, 6);
+              if constexpr (KS) {
+                // ---- k-split: this CTA's two tiles hold the partial sums (first / second half of its half of k) of ALL 64
+                //      rows.  The other CTA's 32 rows go to its receive buffers through distributed shared memory ([row]
+                //      [feature]: a warp stores 128 contiguous bytes), the own 32 rows stay in registers.  The first tile
+                //      is handed over while the tensor core still works on the second: only the second hand-over is exposed ----
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                  if (m == 0) mbar_wait(&sm.dhalf, layers & 1); else mbar_wait(&sm.dfull, layers & 1);
+                  tc_fence_after();
+                  if (tid == 0 && m == 1) trace_ev(p, g * 4 + l - 1, 7);
+                  // the peer's rows first (it waits for them); the loads of the own rows are in flight while those go out
+                  float tmp[32], tmp2[32];
+                  const int cp = RT * (kh ^ 1), co = RT * kh;
+                  if (x3) {
+                    tmem_ld32x2(taddr + m * C::kAccCols + cp, taddr + m * C::kAccCols + XR + cp, tmp, tmp2);
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) tmp[r] = F16 ? fmaf(tmp2[r], 1.f / kTailScaleF16, tmp[r]) : tmp[r] + tmp2[r];
+                  } else {
+                    tmem_ld32(taddr + m * C::kAccCols + cp, tmp);
+                  }
+                  if (tid == 0 && m == 1) trace_ev(p, g * 4 + l - 1, 11);
+                  uint32_t o1[32], o2[32];
+                  if (x3) tmem_ld32x2_issue(taddr + m * C::kAccCols + co, taddr + m * C::kAccCols + XR + co, o1, o2);
+                  // st.async: every 16-byte store signals its bytes on the peer's barrier when it lands -- no release (which
+                  // would wait for the acknowledgements of the stores before the arrival even leaves)
+#pragma unroll
+                  for (int j = 0; j < RT / 4; ++j)
+                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(
+                                     peer_recv + (uint32_t)((m * kFTU + f) * (RT * 4) + ((j ^ (f & 7)) << 4))),
+                                 "r"(__float_as_uint(tmp[4 * j])), "r"(__float_as_uint(tmp[4 * j + 1])), "r"(__float_as_uint(tmp[4 * j + 2])),
+                                 "r"(__float_as_uint(tmp[4 * j + 3])), "r"(peer_rbar)
+                                 : "memory");
+                  if (tid == 0 && m == 1) trace_ev(p, g * 4 + l - 1, 12);
+                  if (x3) {
+                    tmem_ld32x2_finish(o1, o2, tmp, tmp2);
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) tmp[r] = F16 ? fmaf(tmp2[r], 1.f / kTailScaleF16, tmp[r]) : tmp[r] + tmp2[r];
+                  } else {
+                    tmem_ld32(taddr + m * C::kAccCols + co, tmp);
+                  }
+                  if (tid == 0 && m == 1) trace_ev(p, g * 4 + l - 1, 13);
+#pragma unroll
+                  for (int r = 0; r < 32; ++r) v[r] = m == 0 ? tmp[r] : v[r] + tmp[r];
+                }
+              } else {
               mbar_wait(&sm.dfull, layers & 1);
               tc_fence_after();
               if (tid == 0) trace_ev(p, g * 4 + l - 1, 7);
-              if constexpr (KS) {
-                // ---- k-split: this CTA's tiles hold the partial sums (its half of k) of ALL 64 rows.  The other CTA's 32
-                //      rows go to its receive buffer through distributed shared memory ([row][feature]: a warp stores 128
-                //      contiguous bytes), the own 32 rows stay in registers and get the peer's half added ----
-                float other[RT];
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {  // hh = 0: the peer's rows, 1: the own rows
-                  const int c0 = hh == 0 ? RT * (kh ^ 1) : RT * kh;
-#pragma unroll
-                  for (int m = 0; m < kAcc; ++m) {
-                    if (m >= KCHL) break;
-                    float tmp[32], tmp2[32];
-                    tmem_ld32(taddr + m * C::kAccCols + c0, tmp);
-                    if (x3) {
-                      tmem_ld32(taddr + m * C::kAccCols + XR + c0, tmp2);
-#pragma unroll
-                      for (int r = 0; r < 32; ++r) tmp[r] = F16 ? fmaf(tmp2[r], 1.f / kTailScaleF16, tmp[r]) : tmp[r] + tmp2[r];
-                    }
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) {
-                      if (hh == 0) other[r] = m == 0 ? tmp[r] : other[r] + tmp[r];
-                      else v[r] = m == 0 ? tmp[r] : v[r] + tmp[r];
-                    }
-                  }
-                  if (hh == 0) {
-#pragma unroll
-                    for (int r = 0; r < RT; ++r)
-                      asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(peer_recv + (uint32_t)((r * kFTU + f) * 4)), "f"(other[r]) : "memory");
-                    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_rbar) : "memory");
-                  }
-                }
-              } else {
 #pragma unroll
               for (int c0 = 0; c0 < ER; c0 += 32) {
                 // the accumulator tiles (k-chunks i = m mod kAcc), added in a fixed order
@@ -1153,11 +1214,14 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
                 for (int m = 0; m < kAcc; ++m) {
                   if (m >= KCH) break;  // a layer of fewer chunks than tiles (hidden = 128) leaves the rest untouched
                   float tmp[32], tmp2[32];
-                  tmem_ld32(taddr + m * C::kAccCols + row0 + c0, tmp);  // bf16x3: W_head*A_head + W_tail*A_head; fp16x3: W_head*A_head
+                  // main: bf16x3 W_head*A_head + W_tail*A_head, fp16x3 W_head*A_head; second: bf16x3 W_head*A_tail, fp16x3
+                  // 2^11 (W_head*A_tail + W_tail*A_head)
                   if (x3) {
-                    tmem_ld32(taddr + m * C::kAccCols + RT + row0 + c0, tmp2);  // bf16x3: W_head*A_tail; fp16x3: 2^11 (W_head*A_tail + W_tail*A_head)
+                    tmem_ld32x2(taddr + m * C::kAccCols + row0 + c0, taddr + m * C::kAccCols + RT + row0 + c0, tmp, tmp2);
 #pragma unroll
                     for (int r = 0; r < 32; ++r) tmp[r] = F16 ? fmaf(tmp2[r], 1.f / kTailScaleF16, tmp[r]) : tmp[r] + tmp2[r];
+                  } else {
+                    tmem_ld32(taddr + m * C::kAccCols + row0 + c0, tmp);
                   }
 #pragma unroll
                   for (int r = 0; r < 32; ++r) v[c0 + r] = m == 0 ? tmp[r] : v[c0 + r] + tmp[r];
@@ -1179,9 +1243,16 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
                     if (!ok && clock64() - tw > 4000000000LL) __trap();
                   }
                 }
-                const uint32_t rv = smem_u32(sm.recv) + (uint32_t)(f * 4);
+                if (tid == 0) trace_ev(p, g * 4 + l - 1, 14);
+                if (tid == 0) mbar_arrive_expect_tx(&sm.rbar, C::kRecvBytes);  // the next layer's phase
+                const uint32_t rv = smem_u32(sm.recv) + (uint32_t)(f * (RT * 4));
 #pragma unroll
-                for (int r = 0; r < RT; ++r) v[r] += lds32(rv + (uint32_t)(r * kFTU * 4));
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                  for (int j = 0; j < RT / 4; ++j) {
+                    const float4 x = lds128(rv + (uint32_t)(m * kFTU * RT * 4 + ((j ^ (f & 7)) << 4)));
+                    v[4 * j] += x.x, v[4 * j + 1] += x.y, v[4 * j + 2] += x.z, v[4 * j + 3] += x.w;
+                  }
               }
               ++layers;
               const float bb = lds32(sp_a + (kSmBigB - C::kSmShift + (l - 1) * kFTU + f) * 4);

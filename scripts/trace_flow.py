@@ -40,7 +40,7 @@ torch.cuda.synchronize()
 _lib.lib().ikf_flow_debug_trace(h, None, 0)
 sa = stamps.cpu().view(NT, nl, EV)
 t0 = int(sa[:, :, :16][sa[:, :, :16] > 0].min())
-T = 8
+T = 16 if os.environ.get('TRACE_PAIRS') else 8
 
 
 def us(v):
@@ -53,6 +53,12 @@ print("layer " + " ".join(f"{n:>9s}" for n in names))
 for i in range(nl):
     print(f"{i:5d} " + " ".join(f"{us(v):9.2f}" for v in sa[0, i, :16]))
 
+if os.environ.get("TRACE_PAIRS"):
+    print("k-split hand-over, CTA 0, us after the layer's accumulators were complete (c:full0): peer rows loaded / sent / own rows loaded / peer's sums arrived / v ready")
+    for i in range(4, nl):
+        if i % 4 < 2:
+            b0 = int(sa[0, i, 7])
+            print(f"  layer {i}: " + " ".join(f"{(int(sa[0, i, e]) - b0) / 1000.0:6.2f}" for e in (11, 12, 13, 14, 9)))
 print("per-subnet duration (coupled -> coupled, CTA 0, us): " + " ".join(f"{(int(sa[0, 4 * s_ + 3, 13]) - int(sa[0, 4 * s_ - 1, 13])) / 1000.0:5.1f}" for s_ in range(1, nsub)))
 print("\nper-CTA stamps (us), subnets 1..:")
 for sub in range(1, min(nsub, 6)):

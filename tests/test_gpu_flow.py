@@ -569,7 +569,7 @@ def test_ksplit_kernel_matches_oracle(batch, precision, monkeypatch):
     plain, _, _ = _model_with_precision(precision)
     ref = plain.inverse(latent.to(DEV), cond.to(DEV))
     assert "ksplit" not in plain.last_kernel()
-    assert (ref - out).abs().max() < 2e-5  # same arithmetic, another summation order
+    assert (ref - out).abs().max() < 4e-5  # same operands, another summation order and accumulator-tile assignment
 
 
 def test_ksplit_kernel_other_shapes_and_directions():
