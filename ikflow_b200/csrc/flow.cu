@@ -107,6 +107,7 @@ struct IkfFlow {
   int last_grid = 0, last_cluster = 1;
   unsigned long long* trace = nullptr;
   int trace_layers = 0;
+  std::vector<int> host_perm;  // [nb][kPad] perm_inv, then [nb][kPad] perm: composed per launch into FlowParams::phys
   size_t smem_bytes = 0;
   // One handle owns ONE exchange workspace (activation ring, partial sums, flags) and one sequence-number space, and a
   // launch occupies every SM (cooperative), so launches of a handle cannot overlap anyway: `mu` serialises the host
@@ -345,6 +346,7 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
       perm[i * kPad + j] = (int)v;
       perm[(nb + i) * kPad + (int)v] = j;  // perm[perm_inv[j]] = j
     }
+  f->host_perm = perm;
   std::vector<float> consts(2 * kPad * kPad + 3 * kPad, 0.f);  // M_inv | b | lo | hi | M
   {
     // FixedLinearTransform forward needs M = M_inv^-1 and logDetM = log|det M|: Gauss-Jordan in double (W <= 16);
@@ -607,6 +609,30 @@ static int flow_launch_locked(IkfFlow* flow, const float* in, int in_ld, const f
   p.out = out; p.out_ld = out_ld; p.out_cols = out_cols; p.batch = batch;
   p.block_first = block_first; p.block_last = block_last; p.finalize = finalize; p.clamp_out = clamp;
   p.forward = forward; p.logdet_out = logdet_out; p.logdet_m = flow->logdet_m;
+  {
+    // PermuteRandom folded into the indexing of the flow state (FlowParams::phys)
+    const int nblk = block_first - block_last + 1;
+    p.fold = (flow->engine && nblk <= kMaxFold) ? 1 : 0;
+    if (p.fold) {
+      const int nb = flow->base.nb_nodes;
+      uint8_t cur[kPad];
+      for (int j = 0; j < kPad; ++j) cur[j] = (uint8_t)j;
+      for (int bi = 0; bi < nblk; ++bi) {
+        const int blk = forward ? block_last + bi : block_first - bi;
+        uint8_t nxt[kPad];
+        if (forward) {  // x[:, perm] before the block: the table of block bi includes its own gather
+          for (int j = 0; j < kPad; ++j) nxt[j] = j < p.W ? cur[flow->host_perm[(size_t)(nb + blk) * kPad + j]] : (uint8_t)j;
+          std::memcpy(cur, nxt, kPad);
+          std::memcpy(p.phys[bi], cur, kPad);
+        } else {        // x[:, perm_inv] after the block
+          std::memcpy(p.phys[bi], cur, kPad);
+          for (int j = 0; j < kPad; ++j) nxt[j] = j < p.W ? cur[flow->host_perm[(size_t)blk * kPad + j]] : (uint8_t)j;
+          std::memcpy(cur, nxt, kPad);
+        }
+      }
+      std::memcpy(p.phys[nblk], cur, kPad);
+    }
+  }
   if (forward && !flow->engine) return fail(IKF_EINVAL, "%s: the forward pass is implemented by the tcgen05 engine only (hidden %% 128 == 0, hidden <= 1024, coeff_fn_config >= 2)", name);
   // Row groups of 32 while that still fits in one wave of teams (more CTAs in flight, and a partner CTA on every SM
   // to compute while a team waits on an exchange), 64 beyond.

@@ -37,6 +37,7 @@ constexpr int kSmallBytes = kSmallFloats * 4;     // 9280, multiple of 16
 static_assert(kSmallBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
 
 constexpr int kMaxPeers = 8;   // GPUs of one node
+constexpr int kMaxFold = 16;   // blocks per launch whose PermuteRandom gathers are folded into the indexing (FlowParams::phys)
 constexpr float kLeakySlope = 0.01f;  // nn.LeakyReLU() default, ikflow/model.py:74-83
 
 struct FlowParams {
@@ -89,6 +90,11 @@ struct FlowParams {
   uint32_t peer_seq;
   uint32_t* peer_counter;           // device counter of finished writer CTAs (monotonic)
   uint32_t peer_count_target;       // its value when the last writer CTA of this launch has counted itself
+  // tcgen05 engine: the PermuteRandom gathers never move the flow state.  phys[i][j] = the column of the state array that
+  // holds logical column j while the i-th block of this launch is evaluated, phys[n_blocks] = at the end (composed on the
+  // host per launch; fold = 0 for launches of more than kMaxFold blocks: those gather physically)
+  int fold;
+  uint8_t phys[kMaxFold + 1][kPad];
   int forward;         // 1: x -> z with log-det (blocks block_last..block_first ascending), tcgen05 engine only
   float logdet_m;      // FixedLinearTransform.logDetM
   float* logdet_out;   // [batch] (forward pass)

@@ -182,6 +182,7 @@ struct __align__(1024) Smem {
   float u[RT][kPad];  // flow state
   float cnd[RT][8];
   float logdet[RT];  // forward pass: log|det J| accumulated over the blocks
+  uint8_t phys[kMaxFold + 1][kPad];  // FlowParams::phys
   // input of the current subnet [state half | condition | 0] at its start, output of its last layer at its end
   float a[RT][kPad];
   uint64_t full[C::kStages], empty[C::kStages];
@@ -1038,6 +1039,8 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
       bar_epi<ET>();
     };
 
+    for (int i = tid; i < (kMaxFold + 1) * kPad; i += ET) sm.phys[i / kPad][i % kPad] = p.fold ? p.phys[i / kPad][i % kPad] : (uint8_t)(i % kPad);
+    // (ordered before its first use by the barriers of the row group's load)
     int g = 0;
     for (int rgi = 0; rgi < my_rgs; ++rgi) {
       const int rg = slot + rgi * p.slots;  // >= n_rowgroups: an empty row group of a cluster in lock step
@@ -1079,7 +1082,10 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
 
       for (int bi = 0; bi < n_blocks; ++bi) {
         const int blk = p.forward ? p.block_last + bi : p.block_first - bi;
-        if (p.forward) permute_state(p.perm_fwd + blk * kPad);  // PermuteRandom forward: x[:, perm], before the block
+        // PermuteRandom (forward: x[:, perm] before the block; reverse: x[:, perm_inv] after it) is folded into the indexing
+        // of the state: logical column j of this block sits in sm.u[.][ph[j]]
+        const uint8_t* ph = sm.phys[p.fold ? bi : 0];
+        if (p.forward && !p.fold) permute_state(p.perm_fwd + blk * kPad);
         for (int step = 0; step < 2; ++step, ++g) {
           const int sidx = p.forward ? 1 - step : step;
           const int sb = g & 1;
@@ -1092,10 +1098,11 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
           // subnet input [state half | condition | 0] (sm.a doubles as this buffer until the last layer)
           for (int i = tid; i < RT * kPad; i += ET) {
             const int r = i / kPad, k = i % kPad;
-            sm.a[r][k] = k < in_len ? sm.u[r][in_off + k] : (k < kin ? sm.cnd[r][k - in_len] : 0.f);
+            sm.a[r][k] = k < in_len ? sm.u[r][ph[in_off + k]] : (k < kin ? sm.cnd[r][k - in_len] : 0.f);
           }
           mbar_wait(&sm.small_full[sb], (g >> 1) & 1);
           bar_epi<ET>();
+          if (tid == 0) trace_ev(p, g * 4, 2);
 
           float v[ER];  // activations of feature f for the rows of this group
           if constexpr (JIT) {
@@ -1127,6 +1134,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
             };
             if (kin <= 12) run(std::integral_constant<int, 12>{});
             else run(std::integral_constant<int, kPad>{});
+            if (tid == 0) trace_ev(p, g * 4, 3);
           } else {
           // ---- first layer: fp32 FMA, one thread per feature (kept for A/B runs: IKFLOW_B200_DEBUG=4096) ----
             const float b0 = lds32(sp_a + (kSmFirstB - C::kSmShift + f) * 4);
@@ -1462,7 +1470,8 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
             const int r = i / tg_len, j = i % tg_len;
             const float sc = p.clamp_scale * atanf(sm.a[r][j]);
             const float tr = sm.a[r][tg_len + j];
-            sm.u[r][tg_off + j] = p.forward ? fmaf(sm.u[r][tg_off + j], expf(sc), tr) : (sm.u[r][tg_off + j] - tr) * expf(-sc);
+            float& uu = sm.u[r][ph[tg_off + j]];
+            uu = p.forward ? fmaf(uu, expf(sc), tr) : (uu - tr) * expf(-sc);
           }
           if (p.forward)  // log-det of the block: sum of the (clamped) scales, one thread per row, fixed order
             for (int r = tid; r < RT; r += ET) {
@@ -1473,10 +1482,11 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
           bar_epi<ET>();
           if (tid == 0) trace_ev(p, g * 4 + 3, 13);
         }
-        if (!p.forward) permute_state(p.perm_inv + blk * kPad);  // PermuteRandom reverse: x[:, perm_inv], after the block
+        if (!p.forward && !p.fold) permute_state(p.perm_inv + blk * kPad);
       }
 
       if (t == 0) {
+        const uint8_t* phf = sm.phys[p.fold ? n_blocks : 0];  // where the logical columns sit at the end
         for (int i = tid; i < RT * p.out_cols; i += ET) {
           const int r = i / p.out_cols, j = i % p.out_cols;
           const int row = rg * XR + xrow0 + r;
@@ -1484,12 +1494,12 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
           float o;
           if (p.finalize) {
             o = 0.f;
-            for (int k = 0; k < p.W; ++k) o = fmaf(sm.u[r][k] - p.flt_b[k], p.m_inv[k * kPad + j], o);
+            for (int k = 0; k < p.W; ++k) o = fmaf(sm.u[r][phf[k]] - p.flt_b[k], p.m_inv[k * kPad + j], o);
             // NaN / inf are reported BEFORE the clamp, and NaN survives it as in torch.clamp (robot.clamp_to_joint_limits)
             if (!isfinite(o)) report_nonfinite(p.status, p.status_host);
             if (p.clamp_out && j < p.ndof && o == o) o = fminf(fmaxf(o, p.lo[j]), p.hi[j]);
           } else {
-            o = sm.u[r][j];
+            o = sm.u[r][phf[j]];
             if (!isfinite(o)) report_nonfinite(p.status, p.status_host);
           }
           p.out[(size_t)row * p.out_ld + j] = o;

@@ -59,6 +59,10 @@ if os.environ.get("TRACE_PAIRS"):
         if i % 4 < 2:
             b0 = int(sa[0, i, 7])
             print(f"  layer {i}: " + " ".join(f"{(int(sa[0, i, e]) - b0) / 1000.0:6.2f}" for e in (11, 12, 13, 14, 9)))
+print("first layer, CTA 0, us after the previous subnet's coupling: input staged / tiles computed+stored / barrier passed / flag released")
+for i in range(4, nl, 4):
+    b0 = int(sa[0, i - 1, 13])
+    print(f"  layer {i}: " + " ".join(f"{(int(sa[0, i, e]) - b0) / 1000.0:6.2f}" for e in (2, 3, 4, 5)))
 print("per-subnet duration (coupled -> coupled, CTA 0, us): " + " ".join(f"{(int(sa[0, 4 * s_ + 3, 13]) - int(sa[0, 4 * s_ - 1, 13])) / 1000.0:5.1f}" for s_ in range(1, nsub)))
 print("\nper-CTA stamps (us), subnets 1..:")
 for sub in range(1, min(nsub, 6)):
