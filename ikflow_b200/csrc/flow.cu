@@ -132,7 +132,7 @@ struct IkfFlow {
     size_t smem = 0;
     const char* name = "";
     int max_slots_cs[5] = {0, 0, 0, 0, 0};  // [cs]: team slots that are co-resident when launched in clusters of cs CTAs (cs = 2, 4)
-  } kern[5];  // [4]: k-split pairs (64-row groups shared by two CTAs per feature tile; tcgen05 only)
+  } kern[6];  // [4]: k-split pairs (64-row groups shared by two CTAs per feature tile), [5]: ping-pong (two 128-row groups per CTA); tcgen05 only
   // tcgen05 engine: CTAs per cluster for the weight multicast across teams (1 = off); IKFLOW_B200_CLUSTER overrides
   // fused gather (ikf_flow_set_peers): peer-mapped gathered buffers / flag arrays of every rank of the node
   int n_ranks = 0, rank = 0;
@@ -143,6 +143,8 @@ struct IkfFlow {
   // k-split pairs for batches of up to ks_slots_max x 64 rows (IKFLOW_B200_KSPLIT=0|1 overrides the default)
   bool ksplit = kDefaultKSplit;
   int ks_slots_max = 0;
+  // ping-pong kernel for batches of more than one wave of 128-row groups (IKFLOW_B200_PP=0|1)
+  bool pingpong = true;
   bool cluster_ok = true;  // cleared if the driver refuses a cooperative launch with clusters
 };
 
@@ -393,7 +395,8 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
 
   // ---- device blob ----
   auto align_up = [](size_t x) { return (x + 1023) & ~(size_t)1023; };
-  const int slots = f->slots_max;  // upper bound; refined below from the occupancy
+  // upper bound, refined below from the occupancy (tcgen05 engine: the ping-pong kernel runs two exchange slots per team)
+  const int slots = engine ? 2 * f->slots_max : f->slots_max;
   const size_t off_big = 0;
   const size_t off_small = align_up(off_big + big_elems * 2);
   const size_t off_jit = align_up(off_small + small_floats * 4);
@@ -453,12 +456,14 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
     f->kern[2] = {(const void*)umma::flow_inverse_umma_kernel<128, false, true>, umma::Cfg<128>::kThreads, f->smem128, "ikf::umma::flow_inverse_umma_kernel<128,false,true>"};
     f->kern[3] = {(const void*)umma::flow_inverse_umma_kernel<32, true, true>, umma::Cfg<32, true>::kThreads, f->smem32j, "ikf::umma::flow_inverse_umma_kernel<32,true,true>"};
     f->kern[4] = {(const void*)umma::flow_inverse_umma_kernel<32, false, true, true>, umma::Cfg<32, false, true>::kThreads, sizeof(umma::Smem<32, false, true>) + 1024, "ikf::umma::flow_inverse_umma_kernel<32,false,true,ksplit>"};
+    f->kern[5] = {(const void*)umma::flow_inverse_umma_kernel<128, false, true, false, true>, umma::Cfg<128, false, false, true>::kThreads, sizeof(umma::Smem<128, false, false, true>) + 1024, "ikf::umma::flow_inverse_umma_kernel<128,false,true,pingpong>"};
   } else if (engine) {
     f->kern[0] = {(const void*)umma::flow_inverse_umma_kernel<32>, umma::Cfg<32>::kThreads, f->smem32, "ikf::umma::flow_inverse_umma_kernel<32,false,false>"};
     f->kern[1] = {(const void*)umma::flow_inverse_umma_kernel<64>, umma::Cfg<64>::kThreads, f->smem64, "ikf::umma::flow_inverse_umma_kernel<64,false,false>"};
     f->kern[2] = {(const void*)umma::flow_inverse_umma_kernel<128>, umma::Cfg<128>::kThreads, f->smem128, "ikf::umma::flow_inverse_umma_kernel<128,false,false>"};
     f->kern[3] = {(const void*)umma::flow_inverse_umma_kernel<32, true>, umma::Cfg<32, true>::kThreads, f->smem32j, "ikf::umma::flow_inverse_umma_kernel<32,true,false>"};
     f->kern[4] = {(const void*)umma::flow_inverse_umma_kernel<32, false, false, true>, umma::Cfg<32, false, true>::kThreads, sizeof(umma::Smem<32, false, true>) + 1024, "ikf::umma::flow_inverse_umma_kernel<32,false,false,ksplit>"};
+    f->kern[5] = {(const void*)umma::flow_inverse_umma_kernel<128, false, false, false, true>, umma::Cfg<128, false, false, true>::kThreads, sizeof(umma::Smem<128, false, false, true>) + 1024, "ikf::umma::flow_inverse_umma_kernel<128,false,false,pingpong>"};
   } else {
     f->kern[0] = {(const void*)flow_inverse_kernel<32>, kThreads, f->smem32, "ikf::flow_inverse_kernel<32>"};
     f->kern[1] = {(const void*)flow_inverse_kernel<64>, kThreads, f->smem64, "ikf::flow_inverse_kernel<64>"};
@@ -466,6 +471,8 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   if (!f->jit) f->kern[3] = IkfFlow::Kernel();
   if (const char* env = std::getenv("IKFLOW_B200_KSPLIT")) f->ksplit = std::atoi(env) != 0;
   if (!f->ksplit || KCH % 4 != 0 || NT > 16) f->kern[4] = IkfFlow::Kernel();  // (flag bits: 2 NT <= 32; whole chunk pairs per half)
+  if (const char* env = std::getenv("IKFLOW_B200_PP")) f->pingpong = std::atoi(env) != 0;
+  if (!f->pingpong || f->kern[5].smem > (size_t)prop.sharedMemPerBlockOptin) f->kern[5] = IkfFlow::Kernel();
   {
     // the teams spin on each other's flags, so every CTA of a launch must be resident: size the slot count from
     // what the device really fits
@@ -649,12 +656,20 @@ static int flow_launch_locked(IkfFlow* flow, const float* in, int in_ld, const f
     p.n_rowgroups = (batch + 63) / 64;
     p.slots = p.n_rowgroups;
   }
-  const IkfFlow::Kernel& k = flow->kern[ks ? 4 : (rt == 32 && flow->jit) ? 3 : rt == 32 ? 0 : rt == 64 ? 1 : 2];
+  // ping-pong (Cfg::PP): two 128-row groups per CTA, as soon as the 128-row groups would not fit one wave of teams
+  const bool pp = flow->engine && flow->kern[5].fn && !flow->forced_rt && !ks && (batch + 127) / 128 > flow->slots_max;
+  if (pp) {
+    rt = 128;
+    p.n_rowgroups = (batch + 127) / 128;
+    p.slots = std::min((p.n_rowgroups + 1) / 2, flow->slots_max);  // teams; each runs the exchange slots 2 s, 2 s + 1
+  }
+  const IkfFlow::Kernel& k = flow->kern[pp ? 5 : ks ? 4 : (rt == 32 && flow->jit) ? 3 : rt == 32 ? 0 : rt == 64 ? 1 : 2];
   // Clusters of cs CTAs = the CTAs with the same feature tile of cs neighbouring teams share every weight chunk by
   // multicast (FlowParams::cluster).  Needs cs teams at least; the slot count becomes a multiple of cs (surplus teams
   // walk empty row groups).
   int cs = 1;
   if (ks) cs = 2;  // (the pair is the cluster; no weight multicast: its CTAs multiply different k-chunks)
+  else if (pp) cs = 1;
   else if (flow->engine && flow->cluster_ok)
     for (int c = (&k == &flow->kern[3]) ? flow->cluster_pref_jit : flow->cluster_pref; c > 1; c >>= 1)
       if (p.n_rowgroups >= c && k.max_slots_cs[c] >= c) {
@@ -683,7 +698,7 @@ static int flow_launch_locked(IkfFlow* flow, const float* in, int in_ld, const f
   p.trace_layers = flow->trace_layers;
   p.debug = flow->debug;
   // every flag of this launch stays below epoch + 1 + (row groups per slot) * (subnets) * (exchanges per subnet)
-  const uint32_t rg_per_slot = (uint32_t)((p.n_rowgroups + p.slots - 1) / p.slots);
+  const uint32_t rg_per_slot = (uint32_t)((p.n_rowgroups + p.slots * (pp ? 2 : 1) - 1) / (p.slots * (pp ? 2 : 1)));
   flow->epoch += rg_per_slot * 2u * (uint32_t)(block_first - block_last + 1) * (uint32_t)(flow->n_big + 1) + 2u;
 
   const int grid = p.slots * flow->NT * (ks ? 2 : 1);

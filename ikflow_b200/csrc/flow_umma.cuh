@@ -103,10 +103,21 @@ __device__ __forceinline__ uint32_t split_one(float v) {
 // what paces the hidden layers) against all 64 rows, hands the partial sums of the other CTA's 32 rows over through
 // distributed shared memory and finishes its own 32 rows: first layer, epilogue, publication, last layer, coupling and
 // flow state are those of a 32-row CTA (RT = 32), at row offset 32 kh inside the team's 64-row exchange tiles.
-template <int RT, bool JIT = false, bool KS = false>
+// PP ("ping-pong", large batches): TWO independent 128-row groups per CTA.  Each has its own four epilogue warps, flow
+// state, accumulator tile (TMEM columns 256 h ..), exchange slot and flags; loaders, MMA warp and the operand rings are
+// shared and walk the layer jobs in the fixed order (step g, layer l, group h).  While the tensor core multiplies a layer
+// of one group, the SIMT phases of the other (drain, publish, last layer, partial sums, coupling, first layer) run --
+// phases during which the tensor core of the single-group kernels idles (half of the time at 128 rows).  A group's four
+// warps take its 128 rows in two passes of 64.
+template <int RT, bool JIT = false, bool KS = false, bool PP = false>
 struct Cfg {
   static_assert(!JIT || RT == 32, "the just-in-time first layer is written for 32-row groups");
   static_assert(!KS || (RT == 32 && !JIT), "k-split pairs: 32 rows per CTA, exchanged first layer");
+  static_assert(!PP || (RT == 128 && !JIT && !KS), "ping-pong: two 128-row groups per CTA");
+  static constexpr bool kPP = PP;
+  static constexpr int kPasses = PP ? 2 : 1;                  // passes of kEpiRows rows a group's warps make over its rows
+  static constexpr int kStateRows = PP ? 2 * RT : RT;         // rows of flow state held by the CTA
+  static constexpr int kDomThreads = PP ? 128 : (RT > 64 ? 256 : 128);  // epilogue threads that synchronise with each other
   static constexpr int kXRows = KS ? 2 * RT : RT;     // rows of the exchanged activation tiles = rows of the MMA
   static constexpr int kAPlane = kXRows * kKC * 2;    // one bf16 plane of an activation k-chunk [rows][64]
   static constexpr int kAChunk = 2 * kAPlane;        // head + tail
@@ -131,7 +142,7 @@ struct Cfg {
   // which is idle while it is needed (nothing is exchanged between the end of a subnet's second hidden layer and the
   // publication of the next subnet's first layer).
   static constexpr bool kSplit = !JIT;
-  static constexpr int kWStages = (RT == 128 || KS) ? 3 : 4;
+  static constexpr int kWStages = PP ? 2 : ((RT == 128 || KS) ? 3 : 4);
   static constexpr int kAStages = RT == 128 ? 2 : ((RT == 64 || KS) ? 3 : 4);
   static constexpr int kRecvBytes = KS ? 2 * RT * kFTU * 4 : 16;  // k-split: the peer's partial sums of this CTA's rows, 2 x [32][128] fp32
   // loader warp w owns the ring stages s with s % kLoaders == w: its waits on a stage's barriers are then strictly in
@@ -164,33 +175,34 @@ struct Cfg {
   static_assert(kMmaWarps * kAccCols <= 512, "TMEM has 512 columns");
   static_assert(kStage % 1024 == 0, "stages must keep the 1024-byte alignment of the swizzle atoms");
   static_assert(kAChunk % 1024 == 0, "stages must keep the 1024-byte alignment of the swizzle atoms");
-  static_assert(JIT || kGroups * kVtBytes <= kAStages * kAChunk, "the last layer's scratch must fit the activation ring");
+  static_assert(JIT || PP || kGroups * kVtBytes <= kAStages * kAChunk, "the last layer's scratch must fit the activation ring");
 };
 
-template <int RT, bool JIT = false, bool KS = false>
+template <int RT, bool JIT = false, bool KS = false, bool PP = false>
 struct __align__(1024) Smem {
-  using C = Cfg<RT, JIT, KS>;
+  using C = Cfg<RT, JIT, KS, PP>;
   // JIT kernel: unified ring [weights head|tail][activations head|tail][first-layer weights]; the others: split rings
   uint8_t ring[JIT ? C::kStages : 1][JIT ? C::kStage : 1024];
   uint8_t wring[JIT ? 1 : C::kWStages][JIT ? 1024 : kWChunkU];   // [head | tail] x [128 features][64 k]
   uint8_t aring[JIT ? 1 : C::kAStages][JIT ? 1024 : C::kAChunk];  // [head | tail] x [RT rows][64 k]
   // per epilogue group: fp32 activations [32 rows][128 features] for the last layer (float4 slots swizzled); the kernels
   // with split rings keep it in `aring` instead
-  uint8_t vt[JIT ? C::kGroups : 1][JIT ? C::kVtBytes : 1024];
+  uint8_t vt[JIT ? C::kGroups : 1][(JIT || PP) ? C::kVtBytes : 1024];  // (ping-pong: ONE tile, taken in turn -- vt_lock)
   uint8_t recv[C::kRecvBytes];  // k-split: written by the peer CTA of the cluster (st.async), 2 x [128 features][32 rows] fp32, 16-byte units swizzled
   float small[2][C::kSmFloats];
-  float u[RT][kPad];  // flow state
-  float cnd[RT][8];
-  float logdet[RT];  // forward pass: log|det J| accumulated over the blocks
+  float u[C::kStateRows][kPad];  // flow state (ping-pong: group h at rows RT h ..)
+  float cnd[C::kStateRows][8];
+  float logdet[C::kStateRows];  // forward pass: log|det J| accumulated over the blocks
   uint8_t phys[kMaxFold + 1][kPad];  // FlowParams::phys
   // input of the current subnet [state half | condition | 0] at its start, output of its last layer at its end
-  float a[RT][kPad];
+  float a[C::kStateRows][kPad];
   uint64_t full[C::kStages], empty[C::kStages];
   uint64_t wfull[C::kWStages], wempty[C::kWStages], afull[C::kAStages], aempty[C::kAStages];  // split rings
   uint64_t w1full[C::kStages];   // JIT: the first-layer weights of the stage's chunk have landed
   uint64_t w1empty[C::kStages];  // JIT: ... and have been used (the stage's weight/activation areas may still be busy)
   uint64_t small_full[2], small_empty[2];
-  uint64_t dfull, dempty;
+  uint64_t dfull[2], dempty[2];  // per group (ping-pong: two)
+  int vt_lock;
   uint64_t rbar;   // k-split: "the peer's partial sums have arrived" (one phase per hidden layer, 32 KB of st.async bytes)
   uint64_t dhalf;  // k-split: the accumulator tile of the first half of the chunks is complete
   uint32_t tmem_base;
@@ -490,9 +502,9 @@ __device__ __forceinline__ void first_layer_tile(uint32_t w_a, uint32_t b_a, con
   if (F16 && vmax > 65504.f) report_range(status, status_host);
 }
 
-template <int RT, bool JIT = false, bool F16 = false, bool KS = false>
-__global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_umma_kernel(const FlowParams p) {
-  using C = Cfg<RT, JIT, KS>;
+template <int RT, bool JIT = false, bool F16 = false, bool KS = false, bool PP = false>
+__global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_inverse_umma_kernel(const FlowParams p) {
+  using C = Cfg<RT, JIT, KS, PP>;
   constexpr int XR = C::kXRows;  // rows of a row group (of the exchanged tiles, of the MMAs); RT = rows this CTA finishes
   constexpr int kStages = C::kStages;
   constexpr int G = C::kGroups, ER = C::kEpiRows, ET = C::kEpiThreads;
@@ -504,11 +516,12 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
   // them in fp32 round-to-nearest.
   // k-split: always two tiles, the first and the second half of the CTA's chunks (the first half is handed over to the peer
   // while the second is still being multiplied); 8 chunks per layer and CTA -> the same 16 steps per tile as above
-  constexpr int kAcc = KS ? 2 : (F16 ? (XR == 128 ? 2 : 4) : 1);
-  constexpr int kTmemColsK = kAcc * C::kAccCols <= 32 ? 32 : (kAcc * C::kAccCols <= 64 ? 64 : (kAcc * C::kAccCols <= 128 ? 128 : (kAcc * C::kAccCols <= 256 ? 256 : 512)));
+  constexpr int kAcc = KS ? 2 : (PP ? 1 : (F16 ? (XR == 128 ? 2 : 4) : 1));  // ping-pong: the second tile belongs to the other group
+  constexpr int NG = PP ? 2 : 1;  // independent row groups per CTA
+  constexpr int kTmemColsK = PP ? 512 : kAcc * C::kAccCols <= 32 ? 32 : (kAcc * C::kAccCols <= 64 ? 64 : (kAcc * C::kAccCols <= 128 ? 128 : (kAcc * C::kAccCols <= 256 ? 256 : 512)));
   static_assert(kAcc * C::kAccCols <= 512 && C::kMmaWarps == 1, "TMEM has 512 columns; the tiles are dealt by chunk index");
   extern __shared__ uint8_t smem_raw[];
-  Smem<RT, JIT, KS>& sm = *reinterpret_cast<Smem<RT, JIT, KS>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Smem<RT, JIT, KS, PP>& sm = *reinterpret_cast<Smem<RT, JIT, KS, PP>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -544,8 +557,11 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
       mbar_init(&sm.small_full[b], 1);
       mbar_init(&sm.small_empty[b], C::kEpiWarps);
     }
-    mbar_init(&sm.dfull, C::kMmaWarps);
-    mbar_init(&sm.dempty, C::kEpiWarps);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.dfull[i], C::kMmaWarps);
+      mbar_init(&sm.dempty[i], PP ? C::kEpiWarps / 2 : C::kEpiWarps);
+    }
+    sm.vt_lock = 0;
     mbar_init(&sm.rbar, 1);
     if (KS) mbar_arrive_expect_tx(&sm.rbar, C::kRecvBytes);  // first phase: two hand-overs of [32 rows][128 features] fp32
     mbar_init(&sm.dhalf, 1);
@@ -564,15 +580,20 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  uint8_t* act_slot = p.act + (size_t)slot * 2 * NT * kAStrideU;
-  uint8_t* part_slot = reinterpret_cast<uint8_t*>(p.partial) + (size_t)slot * 2 * NT * kRTMaxU * kPartRowBytes;
-  uint32_t* aflag = p.act_flag + (size_t)slot * 2 * NT * FW;  // [2 buffers][NT tiles][FW]
+  // exchange scratch and flags of group h's (virtual) team slot; ping-pong: team `slot` runs the slots 2 slot, 2 slot + 1
+  auto act_slot_of = [&](int h) { return p.act + (size_t)(PP ? 2 * slot + h : slot) * 2 * NT * kAStrideU; };
+  auto part_slot_of = [&](int h) {
+    return reinterpret_cast<uint8_t*>(p.partial) + (size_t)(PP ? 2 * slot + h : slot) * 2 * NT * kRTMaxU * kPartRowBytes;
+  };
+  auto aflag_of = [&](int h) { return p.act_flag + (size_t)(PP ? 2 * slot + h : slot) * 2 * NT * FW; };  // [2 buffers][NT tiles][FW]
 
   const int n_blocks = p.block_first - p.block_last + 1;
   const int steps_per_rg = 2 * n_blocks;
   // clusters keep their CTAs in lock step (the weight stream is shared): every team then walks the same number of row
   // groups, the last ones possibly empty (rows >= batch read as zeros and are not written)
-  const int my_rgs = p.cluster > 1 ? (p.n_rowgroups + p.slots - 1) / p.slots : (p.n_rowgroups - slot + p.slots - 1) / p.slots;
+  // (ping-pong: both groups of every CTA walk the same number of row groups, for the shared loaders' and the MMA warp's sake)
+  const int my_rgs = PP ? (p.n_rowgroups + 2 * p.slots - 1) / (2 * p.slots)
+                        : p.cluster > 1 ? (p.n_rowgroups + p.slots - 1) / p.slots : (p.n_rowgroups - slot + p.slots - 1) / p.slots;
   const int total_steps = my_rgs * steps_per_rg;
 
   // Just-in-time first layer of subnet step g: generation warp j (epilogue warps 0-3, helper warps 4-7) runs over the
@@ -683,6 +704,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
           for (int l = 0; l < p.n_big; ++l) {
             const uint8_t* wbase =
                 reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n * p.n_big + l) * NT + t) * KCH * kWChunkU;
+            for (int hh = 0; hh < NG; ++hh)  // ping-pong: the layer's weights once per group (the groups are out of phase)
             for (int i = 0; i < KCHL; ++i, ++pos) {
               const int st = pos % C::kWStages;
               const uint32_t use = pos / C::kWStages;
@@ -700,11 +722,11 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
                 } else {
                   bulk_g2s(sm.wring[st], wbase + (size_t)kc * kWChunkU, kWChunkU, &sm.wfull[st]);
                 }
-                if (i == 0) trace_ev(p, g * 4 + l, 0);
+                if (i == 0 && hh == 0) trace_ev(p, g * 4 + l, 0);
               }
               __syncwarp();
               if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 80 + i);
-              if (i == 0) {  // after the layer's first copy is on its way: next layers into L2
+              if (i == 0 && hh == 0) {  // after the layer's first copy is on its way: next layers into L2
                 const int q = g * p.n_big + l;
                 const int dist = (p.debug & 32) ? 0 : (p.debug & 64) ? 1 : (p.debug & 128) ? 3 : (p.debug & 256) ? 4 : 2;
                 if (q == 0) for (int d = 1; d < dist; ++d) prefetch_layer(d);
@@ -718,12 +740,14 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
       } else {
         uint32_t pos = 0;
         bool gave_up = false;
+        uint32_t act_wg[2][2] = {{0, 0}, {0, 0}}, xchgg[2] = {0, 0};  // per group
         for (int g = 0; g < total_steps; ++g) {
-          for (int l = 0; l < p.n_big; ++l) {
-            const int buf = xchg & 1;
-            const uint32_t expected = p.epoch + 1 + act_w[buf];
-            const uint8_t* abase = act_slot + (size_t)buf * NT * kAStrideU;
-            const uint32_t* my_flag = aflag + buf * NT * FW + (lane < NT * FW ? lane : 0);
+          for (int l = 0; l < p.n_big; ++l)
+          for (int hh = 0; hh < NG; ++hh) {
+            const int buf = xchgg[hh] & 1;
+            const uint32_t expected = p.epoch + 1 + act_wg[hh][buf];
+            const uint8_t* abase = act_slot_of(hh) + (size_t)buf * NT * kAStrideU;
+            const uint32_t* my_flag = aflag_of(hh) + buf * NT * FW + (lane < NT * FW ? lane : 0);
             uint32_t ready = gave_up ? 0xffffffffu : 0u;  // bit: that producer CTA has published (warp-uniform); k-split: two per tile
             for (int i = 0; i < KCHL; ++i, ++pos) {
               const int st = pos % C::kAStages;
@@ -763,14 +787,13 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
               if (lane == st) {
                 mbar_arrive_expect_tx(&sm.afull[st], C::kAChunk);
                 bulk_g2s(sm.aring[st], abase + (size_t)c * kAStrideU + (size_t)(kc & 1) * C::kAChunk, C::kAChunk, &sm.afull[st]);
-                if (i == 0) trace_ev(p, g * 4 + l, 1);
-                if (i == KCH - 1) trace_ev(p, g * 4 + l, 2);
+                if (i == 0 && hh == 0) trace_ev(p, g * 4 + l, 1);
               }
               __syncwarp();
               if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 48 + i);
             }
-            ++act_w[buf];
-            ++xchg;
+            ++act_wg[hh][buf];
+            ++xchgg[hh];
           }
         }
       }
@@ -784,8 +807,8 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
           const uint32_t expected = p.epoch + 1 + act_w[buf];
           const uint8_t* wbase =
               reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n * p.n_big + l) * NT + t) * KCH * kWChunkU;
-          const uint8_t* abase = act_slot + (size_t)buf * NT * kAStrideU;
-          const uint32_t* my_flag = aflag + buf * NT + (lane < NT ? lane : 0);
+          const uint8_t* abase = act_slot_of(0) + (size_t)buf * NT * kAStrideU;
+          const uint32_t* my_flag = aflag_of(0) + buf * NT + (lane < NT ? lane : 0);
           bool prefetched = lw != C::kLoaders - 1;  // the last loader warp pulls weights into L2, see prefetch_layer
           // JIT: the activations of the first hidden layer are written into the stage by this CTA's own SIMT warps;
           // the loader brings the first-layer weights of the chunk's 64 features instead, and nothing is exchanged
@@ -920,7 +943,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
       constexpr uint32_t idesc = make_idesc(kFTU, XR, F16);       // N = rows of the row group
       constexpr uint32_t idesc2 = make_idesc(kFTU, 2 * XR, F16);  // N = 2 x rows: activation head and tail stacked
       uint32_t ring_pos = 0;
-      uint32_t layers = 0;  // hidden layers issued so far
+      uint32_t layers[2] = {0, 0};  // hidden layers issued so far, per group
       const bool x3 = p.precision != IKF_PRECISION_BF16X1;
       const uint64_t d_wh0 = make_desc(smem_u32(sm.ring[0])), d_wl0 = make_desc(smem_u32(sm.ring[0]) + kWPlaneU);
       const uint64_t d_a0 = make_desc(smem_u32(sm.ring[0]) + kWChunkU);
@@ -928,8 +951,9 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
       const uint32_t tmem_u0 = __shfl_sync(0xffffffffu, tmem, 0);
       constexpr uint32_t kCorrOff = F16 ? XR : 0;  // fp16x3: the scaled correction terms have their own accumulator
       for (int g = 0; g < total_steps; ++g) {
-        for (int l = 0; l < p.n_big; ++l) {
-          if (layers > 0) mbar_wait(&sm.dempty, (layers - 1) & 1);  // the epilogue has drained the accumulators
+        for (int l = 0; l < p.n_big; ++l)
+        for (int hh = 0; hh < NG; ++hh) {  // ping-pong: the layer jobs alternate between the two groups
+          if (layers[hh] > 0) mbar_wait(&sm.dempty[hh], (layers[hh] - 1) & 1);  // the epilogue has drained the accumulators
           tc_fence_after();
           if constexpr (C::kSplit) {
             // split rings: chunk number ring_pos + i sits in weight stage (ring_pos + i) % kWStages and activation stage
@@ -941,13 +965,13 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
               mbar_wait(&sm.wfull[sw], (pos / C::kWStages) & 1);
               mbar_wait(&sm.afull[sa], (pos / C::kAStages) & 1);
               tc_fence_after();
-              if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 16 + i);
+              if (p.trace != nullptr && lane == 0 && i < 16 && hh == 0) trace_clk(p, g * 4 + l, 16 + i);
               const uint64_t dwh = d_w0 + (uint64_t)(sw * (kWChunkU >> 4)), da = d_as0 + (uint64_t)(sa * (C::kAChunk >> 4));
               if (elect_one()) {
                 // accumulator tile of this chunk (k-split: first / second half of the CTA's chunks)
                 const int tile = KS ? (i >= KCHL / 2 ? 1 : 0) : i % kAcc;
                 const bool accum = KS ? (i != 0 && i != KCHL / 2) : i >= kAcc;
-                const uint32_t tmem_u = tmem_u0 + (uint32_t)(tile * C::kAccCols);
+                const uint32_t tmem_u = tmem_u0 + (uint32_t)(tile * C::kAccCols) + (PP ? (uint32_t)(hh * C::kAccCols) : 0u);
                 if (x3)
                   mma_chunk_x3(tmem_u, tmem_u + kCorrOff, idesc2, idesc, dwh, dwh + (uint64_t)(kWPlaneU >> 4), da, accum);
                 else
@@ -989,10 +1013,10 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
               ring_pos += kStages;
             }
           }
-          if (elect_one()) mma_commit(&sm.dfull);  // accumulator complete
+          if (elect_one()) mma_commit(&sm.dfull[hh]);  // accumulator complete
           __syncwarp();
-          if (lane == 0) trace_ev(p, g * 4 + l, 8);
-          ++layers;
+          if (lane == 0 && hh == 0) trace_ev(p, g * 4 + l, 8);
+          ++layers[hh];
         }
       }
     }
@@ -1002,17 +1026,32 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
     const int h = tid >> 7;    // epilogue group: rows h*ER .. h*ER + ER - 1
     const int sub = f >> 6;    // which of the CTA's two 64-wide k-chunks
     const int kf = f & 63;
-    const int row0 = h * ER;
-    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    // Synchronisation domain: all epilogue threads -- or, ping-pong, the 128 threads of this thread's row group, which has
+    // its own flow state, accumulator tile, exchange slot and flags and runs out of phase with the other group
+    constexpr int DT = C::kDomThreads;
+    const int dt = PP ? f : tid;  // index inside the domain
+    const int gh = PP ? h : 0;    // this thread's row group inside the CTA
+    auto bar_dom = [&]() {
+      if constexpr (PP) bar_group(h); else bar_epi<ET>();
+    };
+    float (*su)[kPad] = sm.u + (PP ? h * RT : 0);
+    float (*sa)[kPad] = sm.a + (PP ? h * RT : 0);
+    float (*scnd)[8] = sm.cnd + (PP ? h * RT : 0);
+    float* sld = sm.logdet + (PP ? h * RT : 0);
+    uint8_t* const act_slot = act_slot_of(gh);
+    uint8_t* const part_slot = part_slot_of(gh);
+    uint32_t* const aflag = aflag_of(gh);
+    int row0 = PP ? 0 : h * ER;   // first row of the thread's current 64 (ping-pong: of the current pass)
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (PP ? (uint32_t)(h * C::kAccCols) : 0u);
     uint32_t part_w[2] = {0, 0};
     uint32_t pxchg = 0;
     uint32_t act_w[2] = {0, 0};  // publishes so far into each activation scratch buffer
     uint32_t axchg = 0;          // activation exchanges so far
     uint32_t layers = 0;         // hidden layers drained so far
     const bool x3 = p.precision != IKF_PRECISION_BF16X1;
-    const uint32_t vt_a = JIT ? smem_u32(sm.vt[h]) : smem_u32(&sm.aring[0][0]) + h * C::kVtBytes;
+    const uint32_t vt_a = PP ? smem_u32(sm.vt[0]) : JIT ? smem_u32(sm.vt[h]) : smem_u32(&sm.aring[0][0]) + h * C::kVtBytes;
     const int j8 = lane & 7;     // publish: row inside an 8-row block after the lane transpose
-    const uint32_t xin_a = smem_u32(&sm.a[0][0]);
+    const uint32_t xin_a = smem_u32(&sa[0][0]);
     const bool tiled_first = !JIT && (KS || !(p.debug & 4096));
     // k-split: shared::cluster addresses of the peer CTA's receive buffer and barrier
     uint32_t peer_recv = 0, peer_rbar = 0;
@@ -1023,28 +1062,30 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
 
     // u <- u[:, table]
     auto permute_state = [&](const int* table) {
-      constexpr int kPer = (RT * kPad + ET - 1) / ET;
+      constexpr int kPer = (RT * kPad + DT - 1) / DT;
       float tmp[kPer];
 #pragma unroll
       for (int c = 0; c < kPer; ++c) {
-        const int i = tid + c * ET;
-        tmp[c] = i < RT * p.W ? sm.u[i / p.W][table[i % p.W]] : 0.f;
+        const int i = dt + c * DT;
+        tmp[c] = i < RT * p.W ? su[i / p.W][table[i % p.W]] : 0.f;
       }
-      bar_epi<ET>();
+      bar_dom();
 #pragma unroll
       for (int c = 0; c < kPer; ++c) {
-        const int i = tid + c * ET;
-        if (i < RT * p.W) sm.u[i / p.W][i % p.W] = tmp[c];
+        const int i = dt + c * DT;
+        if (i < RT * p.W) su[i / p.W][i % p.W] = tmp[c];
       }
-      bar_epi<ET>();
+      bar_dom();
     };
 
-    for (int i = tid; i < (kMaxFold + 1) * kPad; i += ET) sm.phys[i / kPad][i % kPad] = p.fold ? p.phys[i / kPad][i % kPad] : (uint8_t)(i % kPad);
-    // (ordered before its first use by the barriers of the row group's load)
+    // (every synchronisation domain writes the whole table -- identical values --, so that the barriers of its own row
+    // group's load order the writes before the first use)
+    for (int i = dt; i < (kMaxFold + 1) * kPad; i += DT) sm.phys[i / kPad][i % kPad] = p.fold ? p.phys[i / kPad][i % kPad] : (uint8_t)(i % kPad);
     int g = 0;
     for (int rgi = 0; rgi < my_rgs; ++rgi) {
-      const int rg = slot + rgi * p.slots;  // >= n_rowgroups: an empty row group of a cluster in lock step
-      for (int i = tid; i < RT * kPad; i += ET) {
+      // (>= n_rowgroups: an empty row group of a cluster / of a ping-pong CTA in lock step)
+      const int rg = PP ? 2 * slot + h + rgi * 2 * p.slots : slot + rgi * p.slots;
+      for (int i = dt; i < RT * kPad; i += DT) {
         const int r = i / kPad, j = i % kPad;
         const int row = rg * XR + xrow0 + r;
         float uv = 0.f, cv = 0.f;
@@ -1052,38 +1093,38 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
           if (j < p.W) uv = p.in[(size_t)row * p.in_ld + j];
           if (j < p.cond_cols) cv = p.cond[(size_t)(row % p.cond_rows) * p.cond_ld + j];
         }
-        sm.u[r][j] = uv;
-        if (j < 8) sm.cnd[r][j] = cv;
+        su[r][j] = uv;
+        if (j < 8) scnd[r][j] = cv;
       }
-      bar_epi<ET>();
+      bar_dom();
       if (p.forward) {
         // FixedLinearTransform forward, x.mm(M) + b (FrEIA; ikflow/model.py:197), and a fresh log-det accumulator
-        constexpr int kPer = (RT * kPad + ET - 1) / ET;
+        constexpr int kPer = (RT * kPad + DT - 1) / DT;
         float tmp[kPer];
 #pragma unroll
         for (int c = 0; c < kPer; ++c) {
-          const int i = tid + c * ET, r = i / kPad, j = i % kPad;
+          const int i = dt + c * DT, r = i / kPad, j = i % kPad;
           float o = 0.f;
           if (i < RT * kPad && j < p.W) {
-            for (int k = 0; k < p.W; ++k) o = fmaf(sm.u[r][k], p.m_fwd[k * kPad + j], o);
+            for (int k = 0; k < p.W; ++k) o = fmaf(su[r][k], p.m_fwd[k * kPad + j], o);
             o += p.flt_b[j];
           }
           tmp[c] = o;
         }
-        bar_epi<ET>();
+        bar_dom();
 #pragma unroll
         for (int c = 0; c < kPer; ++c) {
-          const int i = tid + c * ET;
-          if (i < RT * kPad) sm.u[i / kPad][i % kPad] = tmp[c];
+          const int i = dt + c * DT;
+          if (i < RT * kPad) su[i / kPad][i % kPad] = tmp[c];
         }
-        for (int r = tid; r < RT; r += ET) sm.logdet[r] = p.logdet_m;
-        bar_epi<ET>();
+        for (int r = dt; r < RT; r += DT) sld[r] = p.logdet_m;
+        bar_dom();
       }
 
       for (int bi = 0; bi < n_blocks; ++bi) {
         const int blk = p.forward ? p.block_last + bi : p.block_first - bi;
         // PermuteRandom (forward: x[:, perm] before the block; reverse: x[:, perm_inv] after it) is folded into the indexing
-        // of the state: logical column j of this block sits in sm.u[.][ph[j]]
+        // of the state: logical column j of this block sits in su[.][ph[j]]
         const uint8_t* ph = sm.phys[p.fold ? bi : 0];
         if (p.forward && !p.fold) permute_state(p.perm_fwd + blk * kPad);
         for (int step = 0; step < 2; ++step, ++g) {
@@ -1096,12 +1137,12 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
           const int tg_len = sidx == 0 ? p.s2 : p.s1;
           const int kin = in_len + p.dim_cond;
           // subnet input [state half | condition | 0] (sm.a doubles as this buffer until the last layer)
-          for (int i = tid; i < RT * kPad; i += ET) {
+          for (int i = dt; i < RT * kPad; i += DT) {
             const int r = i / kPad, k = i % kPad;
-            sm.a[r][k] = k < in_len ? sm.u[r][ph[in_off + k]] : (k < kin ? sm.cnd[r][k - in_len] : 0.f);
+            sa[r][k] = k < in_len ? su[r][ph[in_off + k]] : (k < kin ? scnd[r][k - in_len] : 0.f);
           }
           mbar_wait(&sm.small_full[sb], (g >> 1) & 1);
-          bar_epi<ET>();
+          bar_dom();
           if (tid == 0) trace_ev(p, g * 4, 2);
 
           float v[ER];  // activations of feature f for the rows of this group
@@ -1112,8 +1153,8 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
             jit_layer_loop(0, warp, g, kin);
           } else if (tiled_first) {
             // ---- first layer, tile by tile, published as it is computed (first_layer_tile) ----
-            constexpr int kTilesPerWarp = (RT / 32) * (kFTU / 16) / C::kEpiWarps;
-            const int tile0 = warp * kTilesPerWarp;
+            constexpr int kTilesPerWarp = (RT / 32) * (kFTU / 16) / (PP ? 4 : C::kEpiWarps);  // (ping-pong: the group's four warps)
+            const int tile0 = (PP ? (warp & 3) : warp) * kTilesPerWarp;
             const int rb = tile0 / (kFTU / 16), fb0 = tile0 % (kFTU / 16);
             uint8_t* dst0 = act_slot + ((size_t)(axchg & 1) * NT + t) * kAStrideU;
             const int rb_out = KS ? kh : rb;  // 32-row block inside the exchanged tile (k-split: this CTA's half of the rows)
@@ -1163,158 +1204,258 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
             for (int r = 0; r < ER; ++r) v[r] = leaky(v[r]);
           }
 
+          const int pb = pxchg & 1;
+          const uint32_t pexp = p.epoch + 1 + part_w[pb];  // sequence number of this subnet's partial-sum exchange
+          const int n_units = tg_len;                       // 2 * tg_len outputs, two per 16-byte unit
           for (int l = JIT ? 1 : 0; l <= p.n_big; ++l) {
-            if (l > 0) {
-              // ---- hidden layer l-1: drain the accumulator ----
-              if (tid == 0) trace_ev(p, g * 4 + l - 1, 6);
-              if constexpr (KS) {
-                // ---- k-split: this CTA's two tiles hold the partial sums (first / second half of its half of k) of ALL 64
-                //      rows.  The other CTA's 32 rows go to its receive buffers through distributed shared memory ([row]
-                //      [feature]: a warp stores 128 contiguous bytes), the own 32 rows stay in registers.  The first tile
-                //      is handed over while the tensor core still works on the second: only the second hand-over is exposed ----
-#pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                  if (m == 0) mbar_wait(&sm.dhalf, layers & 1); else mbar_wait(&sm.dfull, layers & 1);
-                  tc_fence_after();
-                  if (tid == 0 && m == 1) trace_ev(p, g * 4 + l - 1, 7);
-                  // the peer's rows first (it waits for them); the loads of the own rows are in flight while those go out
-                  float tmp[32], tmp2[32];
-                  const int cp = RT * (kh ^ 1), co = RT * kh;
-                  if (x3) {
-                    tmem_ld32x2(taddr + m * C::kAccCols + cp, taddr + m * C::kAccCols + XR + cp, tmp, tmp2);
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) tmp[r] = F16 ? fmaf(tmp2[r], 1.f / kTailScaleF16, tmp[r]) : tmp[r] + tmp2[r];
-                  } else {
-                    tmem_ld32(taddr + m * C::kAccCols + cp, tmp);
-                  }
-                  if (tid == 0 && m == 1) trace_ev(p, g * 4 + l - 1, 11);
-                  uint32_t o1[32], o2[32];
-                  if (x3) tmem_ld32x2_issue(taddr + m * C::kAccCols + co, taddr + m * C::kAccCols + XR + co, o1, o2);
-                  // st.async: every 16-byte store signals its bytes on the peer's barrier when it lands -- no release (which
-                  // would wait for the acknowledgements of the stores before the arrival even leaves)
-#pragma unroll
-                  for (int j = 0; j < RT / 4; ++j)
-                    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(
-                                     peer_recv + (uint32_t)((m * kFTU + f) * (RT * 4) + ((j ^ (f & 7)) << 4))),
-                                 "r"(__float_as_uint(tmp[4 * j])), "r"(__float_as_uint(tmp[4 * j + 1])), "r"(__float_as_uint(tmp[4 * j + 2])),
-                                 "r"(__float_as_uint(tmp[4 * j + 3])), "r"(peer_rbar)
-                                 : "memory");
-                  if (tid == 0 && m == 1) trace_ev(p, g * 4 + l - 1, 12);
-                  if (x3) {
-                    tmem_ld32x2_finish(o1, o2, tmp, tmp2);
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) tmp[r] = F16 ? fmaf(tmp2[r], 1.f / kTailScaleF16, tmp[r]) : tmp[r] + tmp2[r];
-                  } else {
-                    tmem_ld32(taddr + m * C::kAccCols + co, tmp);
-                  }
-                  if (tid == 0 && m == 1) trace_ev(p, g * 4 + l - 1, 13);
-#pragma unroll
-                  for (int r = 0; r < 32; ++r) v[r] = m == 0 ? tmp[r] : v[r] + tmp[r];
-                }
-              } else {
-              mbar_wait(&sm.dfull, layers & 1);
+            if (l > 0 && tid == 0) trace_ev(p, g * 4 + l - 1, 6);
+            if (!KS && l > 0) {
+              // ---- hidden layer l-1: its accumulator is complete ----
+              mbar_wait(&sm.dfull[gh], layers & 1);
               tc_fence_after();
               if (tid == 0) trace_ev(p, g * 4 + l - 1, 7);
-#pragma unroll
-              for (int c0 = 0; c0 < ER; c0 += 32) {
-                // the accumulator tiles (k-chunks i = m mod kAcc), added in a fixed order
-#pragma unroll
-                for (int m = 0; m < kAcc; ++m) {
-                  if (m >= KCH) break;  // a layer of fewer chunks than tiles (hidden = 128) leaves the rest untouched
-                  float tmp[32], tmp2[32];
-                  // main: bf16x3 W_head*A_head + W_tail*A_head, fp16x3 W_head*A_head; second: bf16x3 W_head*A_tail, fp16x3
-                  // 2^11 (W_head*A_tail + W_tail*A_head)
-                  if (x3) {
-                    tmem_ld32x2(taddr + m * C::kAccCols + row0 + c0, taddr + m * C::kAccCols + RT + row0 + c0, tmp, tmp2);
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) tmp[r] = F16 ? fmaf(tmp2[r], 1.f / kTailScaleF16, tmp[r]) : tmp[r] + tmp2[r];
-                  } else {
-                    tmem_ld32(taddr + m * C::kAccCols + row0 + c0, tmp);
-                  }
-#pragma unroll
-                  for (int r = 0; r < 32; ++r) v[c0 + r] = m == 0 ? tmp[r] : v[c0 + r] + tmp[r];
-                }
-              }
-              }
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&sm.dempty);
-              if constexpr (KS) {
-                // the peer's partial sums of my rows (one barrier phase per hidden layer, in lock step: neither CTA can run a
-                // layer ahead, it needs the other's publication first)
-                {
-                  uint32_t ok = 0;
-                  const long long tw = clock64();
-                  while (!ok) {
-                    asm volatile("{\n\t.reg .pred pp;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 pp, [%1], %2;\n\tselp.u32 %0, 1, 0, pp;\n\t}"
-                                 : "=r"(ok) : "r"(smem_u32(&sm.rbar)), "r"(layers & 1u) : "memory");
-                    if (!ok && clock64() - tw > 4000000000LL) __trap();
-                  }
-                }
-                if (tid == 0) trace_ev(p, g * 4 + l - 1, 14);
-                if (tid == 0) mbar_arrive_expect_tx(&sm.rbar, C::kRecvBytes);  // the next layer's phase
-                const uint32_t rv = smem_u32(sm.recv) + (uint32_t)(f * (RT * 4));
-#pragma unroll
-                for (int m = 0; m < 2; ++m)
-#pragma unroll
-                  for (int j = 0; j < RT / 4; ++j) {
-                    const float4 x = lds128(rv + (uint32_t)(m * kFTU * RT * 4 + ((j ^ (f & 7)) << 4)));
-                    v[4 * j] += x.x, v[4 * j + 1] += x.y, v[4 * j + 2] += x.z, v[4 * j + 3] += x.w;
-                  }
-              }
-              ++layers;
-              const float bb = lds32(sp_a + (kSmBigB - C::kSmShift + (l - 1) * kFTU + f) * 4);
-#pragma unroll
-              for (int r = 0; r < ER; ++r) v[r] = leaky(v[r] + bb);
-              if (tid == 0) trace_ev(p, g * 4 + l - 1, 9);
             }
-            if (l < p.n_big) {
-              // ---- publish straight from the registers: bf16 head/tail split, 8x8 transpose across the 8 lanes that hold
-              //      8 consecutive features (so that every lane owns one 16-byte chunk = 8 features of one row), two
-              //      16-byte global stores per lane and 8-row block into the producer's slot of the scratch ring
-              //      [k-chunk 2][head|tail][RT rows][64 k, swizzled]; then ONE release flag per CTA ----
-              const int buf = axchg & 1;
-              uint8_t* dst = act_slot + ((size_t)buf * NT + t) * kAStrideU + (size_t)sub * C::kAChunk;
-              const int kf8 = kf & ~7;
-              float pub_max = 0.f;  // fp16x3: largest magnitude published (checked once, after the stores)
-              if (!(l == 0 && tiled_first))  // (the tiled first layer has stored its output already)
-#pragma unroll
-              for (int r0 = 0; r0 < ER; r0 += 8) {
-                uint32_t wd[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  if (F16) pub_max = fmaxf(pub_max, fabsf(v[r0 + i]));
-                  wd[i] = split_one<F16>(v[r0 + i]);  // head in the low half, tail in the high half
+            if (l == p.n_big) {
+              if constexpr (PP) {
+                // the last layer's transposed tile is shared by the two groups (their last layers are half a cycle apart)
+                if (dt == 0) {
+                  const long long tl = clock64();
+                  while (atomicCAS(&sm.vt_lock, 0, 1) != 0) {
+                    __nanosleep(64);
+                    if (clock64() - tl > 4000000000LL) __trap();
+                  }
+                  __threadfence_block();
                 }
-                // before: lane j8 (feature kf8 + j8) holds rows r0..r0+7; after: lane j8 holds row r0 + j8, features kf8..kf8+7
+                bar_dom();
+              }
+              if (tid == 0) trace_ev(p, g * 4 + 3, 11);
+            }
+            float pub_max = 0.f;  // fp16x3: largest magnitude published (checked once, after the stores)
+            const int buf = axchg & 1;
+            // ping-pong: the four warps of a group take its 128 rows in two passes of 64
+#pragma unroll 1
+            for (int pass = 0; pass < C::kPasses; ++pass) {
+              if constexpr (PP) row0 = pass * ER;
+              if (l > 0) {
+                // ---- drain the accumulator (the rows of this pass) ----
+                if constexpr (KS) {
+                  // ---- k-split: this CTA's two tiles hold the partial sums (first / second half of its half of k) of ALL 64
+                  //      rows.  The other CTA's 32 rows go to its receive buffers through distributed shared memory ([row]
+                  //      [feature]: a warp stores 128 contiguous bytes), the own 32 rows stay in registers.  The first tile
+                  //      is handed over while the tensor core still works on the second: only the second hand-over is exposed ----
 #pragma unroll
-                for (int st = 4; st >= 1; st >>= 1) {
+                  for (int m = 0; m < 2; ++m) {
+                    if (m == 0) mbar_wait(&sm.dhalf, layers & 1); else mbar_wait(&sm.dfull[0], layers & 1);
+                    tc_fence_after();
+                    if (tid == 0 && m == 1) trace_ev(p, g * 4 + l - 1, 7);
+                    // the peer's rows first (it waits for them); the loads of the own rows are in flight while those go out
+                    float tmp[32], tmp2[32];
+                    const int cp = RT * (kh ^ 1), co = RT * kh;
+                    if (x3) {
+                      tmem_ld32x2(taddr + m * C::kAccCols + cp, taddr + m * C::kAccCols + XR + cp, tmp, tmp2);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    if ((i & st) == 0) {
-                      const bool up = (j8 & st) != 0;
-                      const uint32_t send = up ? wd[i] : wd[i + st];
-                      const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, st);
-                      if (up) wd[i] = recv; else wd[i + st] = recv;
+                      for (int r = 0; r < 32; ++r) tmp[r] = F16 ? fmaf(tmp2[r], 1.f / kTailScaleF16, tmp[r]) : tmp[r] + tmp2[r];
+                    } else {
+                      tmem_ld32(taddr + m * C::kAccCols + cp, tmp);
+                    }
+                    if (tid == 0 && m == 1) trace_ev(p, g * 4 + l - 1, 11);
+                    uint32_t o1[32], o2[32];
+                    if (x3) tmem_ld32x2_issue(taddr + m * C::kAccCols + co, taddr + m * C::kAccCols + XR + co, o1, o2);
+                    // st.async: every 16-byte store signals its bytes on the peer's barrier when it lands -- no release (which
+                    // would wait for the acknowledgements of the stores before the arrival even leaves)
+#pragma unroll
+                    for (int j = 0; j < RT / 4; ++j)
+                      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(
+                                       peer_recv + (uint32_t)((m * kFTU + f) * (RT * 4) + ((j ^ (f & 7)) << 4))),
+                                   "r"(__float_as_uint(tmp[4 * j])), "r"(__float_as_uint(tmp[4 * j + 1])), "r"(__float_as_uint(tmp[4 * j + 2])),
+                                   "r"(__float_as_uint(tmp[4 * j + 3])), "r"(peer_rbar)
+                                   : "memory");
+                    if (tid == 0 && m == 1) trace_ev(p, g * 4 + l - 1, 12);
+                    if (x3) {
+                      tmem_ld32x2_finish(o1, o2, tmp, tmp2);
+#pragma unroll
+                      for (int r = 0; r < 32; ++r) tmp[r] = F16 ? fmaf(tmp2[r], 1.f / kTailScaleF16, tmp[r]) : tmp[r] + tmp2[r];
+                    } else {
+                      tmem_ld32(taddr + m * C::kAccCols + co, tmp);
+                    }
+                    if (tid == 0 && m == 1) trace_ev(p, g * 4 + l - 1, 13);
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) v[r] = m == 0 ? tmp[r] : v[r] + tmp[r];
+                  }
+                } else {
+#pragma unroll
+                for (int c0 = 0; c0 < ER; c0 += 32) {
+                  // the accumulator tiles (k-chunks i = m mod kAcc), added in a fixed order
+#pragma unroll
+                  for (int m = 0; m < kAcc; ++m) {
+                    if (m >= KCH) break;  // a layer of fewer chunks than tiles (hidden = 128) leaves the rest untouched
+                    float tmp[32], tmp2[32];
+                    // main: bf16x3 W_head*A_head + W_tail*A_head, fp16x3 W_head*A_head; second: bf16x3 W_head*A_tail, fp16x3
+                    // 2^11 (W_head*A_tail + W_tail*A_head)
+                    if (x3) {
+                      tmem_ld32x2(taddr + m * C::kAccCols + row0 + c0, taddr + m * C::kAccCols + RT + row0 + c0, tmp, tmp2);
+#pragma unroll
+                      for (int r = 0; r < 32; ++r) tmp[r] = F16 ? fmaf(tmp2[r], 1.f / kTailScaleF16, tmp[r]) : tmp[r] + tmp2[r];
+                    } else {
+                      tmem_ld32(taddr + m * C::kAccCols + row0 + c0, tmp);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) v[c0 + r] = m == 0 ? tmp[r] : v[c0 + r] + tmp[r];
+                  }
+                }
+                }
+                if (pass == C::kPasses - 1) {
+                  tc_fence_before();
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(&sm.dempty[gh]);
+                }
+                if constexpr (KS) {
+                  // the peer's partial sums of my rows (one barrier phase per hidden layer, in lock step: neither CTA can run a
+                  // layer ahead, it needs the other's publication first)
+                  {
+                    uint32_t ok = 0;
+                    const long long tw = clock64();
+                    while (!ok) {
+                      asm volatile("{\n\t.reg .pred pp;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 pp, [%1], %2;\n\tselp.u32 %0, 1, 0, pp;\n\t}"
+                                   : "=r"(ok) : "r"(smem_u32(&sm.rbar)), "r"(layers & 1u) : "memory");
+                      if (!ok && clock64() - tw > 4000000000LL) __trap();
                     }
                   }
+                  if (tid == 0) trace_ev(p, g * 4 + l - 1, 14);
+                  if (tid == 0) mbar_arrive_expect_tx(&sm.rbar, C::kRecvBytes);  // the next layer's phase
+                  const uint32_t rv = smem_u32(sm.recv) + (uint32_t)(f * (RT * 4));
+#pragma unroll
+                  for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int j = 0; j < RT / 4; ++j) {
+                      const float4 x = lds128(rv + (uint32_t)(m * kFTU * RT * 4 + ((j ^ (f & 7)) << 4)));
+                      v[4 * j] += x.x, v[4 * j + 1] += x.y, v[4 * j + 2] += x.z, v[4 * j + 3] += x.w;
+                    }
                 }
-                const uint32_t off = tile_off_bytes(xrow0 + row0 + r0 + j8, kf8);
-                stg128(dst + off, __byte_perm(wd[0], wd[1], 0x5410), __byte_perm(wd[2], wd[3], 0x5410),
-                       __byte_perm(wd[4], wd[5], 0x5410), __byte_perm(wd[6], wd[7], 0x5410));
-                stg128(dst + C::kAPlane + off, __byte_perm(wd[0], wd[1], 0x7632), __byte_perm(wd[2], wd[3], 0x7632),
-                       __byte_perm(wd[4], wd[5], 0x7632), __byte_perm(wd[6], wd[7], 0x7632));
-                if constexpr (JIT) {  // ... and into this CTA's own ring stages 0 / 1 (the next layer starts at stage 0)
-                  const uint32_t own_a = smem_u32(sm.ring[sub]) + kWChunkU + off;
-                  sts128u(own_a, __byte_perm(wd[0], wd[1], 0x5410), __byte_perm(wd[2], wd[3], 0x5410),
-                          __byte_perm(wd[4], wd[5], 0x5410), __byte_perm(wd[6], wd[7], 0x5410));
-                  sts128u(own_a + C::kAPlane, __byte_perm(wd[0], wd[1], 0x7632), __byte_perm(wd[2], wd[3], 0x7632),
-                          __byte_perm(wd[4], wd[5], 0x7632), __byte_perm(wd[6], wd[7], 0x7632));
+                const float bb = lds32(sp_a + (kSmBigB - C::kSmShift + (l - 1) * kFTU + f) * 4);
+#pragma unroll
+                for (int r = 0; r < ER; ++r) v[r] = leaky(v[r] + bb);
+                if (tid == 0) trace_ev(p, g * 4 + l - 1, 9);
+              }
+              if (l < p.n_big) {
+                // ---- publish straight from the registers: bf16 head/tail split, 8x8 transpose across the 8 lanes that hold
+                //      8 consecutive features (so that every lane owns one 16-byte chunk = 8 features of one row), two
+                //      16-byte global stores per lane and 8-row block into the producer's slot of the scratch ring
+                //      [k-chunk 2][head|tail][RT rows][64 k, swizzled]; then ONE release flag per CTA ----
+                uint8_t* dst = act_slot + ((size_t)buf * NT + t) * kAStrideU + (size_t)sub * C::kAChunk;
+                const int kf8 = kf & ~7;
+                if (!(l == 0 && tiled_first))  // (the tiled first layer has stored its output already)
+#pragma unroll
+                for (int r0 = 0; r0 < ER; r0 += 8) {
+                  uint32_t wd[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    if (F16) pub_max = fmaxf(pub_max, fabsf(v[r0 + i]));
+                    wd[i] = split_one<F16>(v[r0 + i]);  // head in the low half, tail in the high half
+                  }
+                  // before: lane j8 (feature kf8 + j8) holds rows r0..r0+7; after: lane j8 holds row r0 + j8, features kf8..kf8+7
+#pragma unroll
+                  for (int st = 4; st >= 1; st >>= 1) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                      if ((i & st) == 0) {
+                        const bool up = (j8 & st) != 0;
+                        const uint32_t send = up ? wd[i] : wd[i + st];
+                        const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, st);
+                        if (up) wd[i] = recv; else wd[i + st] = recv;
+                      }
+                    }
+                  }
+                  const uint32_t off = tile_off_bytes(xrow0 + row0 + r0 + j8, kf8);
+                  stg128(dst + off, __byte_perm(wd[0], wd[1], 0x5410), __byte_perm(wd[2], wd[3], 0x5410),
+                         __byte_perm(wd[4], wd[5], 0x5410), __byte_perm(wd[6], wd[7], 0x5410));
+                  stg128(dst + C::kAPlane + off, __byte_perm(wd[0], wd[1], 0x7632), __byte_perm(wd[2], wd[3], 0x7632),
+                         __byte_perm(wd[4], wd[5], 0x7632), __byte_perm(wd[6], wd[7], 0x7632));
+                  if constexpr (JIT) {  // ... and into this CTA's own ring stages 0 / 1 (the next layer starts at stage 0)
+                    const uint32_t own_a = smem_u32(sm.ring[sub]) + kWChunkU + off;
+                    sts128u(own_a, __byte_perm(wd[0], wd[1], 0x5410), __byte_perm(wd[2], wd[3], 0x5410),
+                            __byte_perm(wd[4], wd[5], 0x5410), __byte_perm(wd[6], wd[7], 0x5410));
+                    sts128u(own_a + C::kAPlane, __byte_perm(wd[0], wd[1], 0x7632), __byte_perm(wd[2], wd[3], 0x7632),
+                            __byte_perm(wd[4], wd[5], 0x7632), __byte_perm(wd[6], wd[7], 0x7632));
+                  }
+                }
+              } else {
+                // ---- last layer: fp32, through a transposed copy of the activations; every group works on its own rows, 32
+                //      at a time ----
+                {
+                  // thread = (k quarter kq, row pair rp, output group og): 2 rows x 8 outputs over 32 of the 128 features,
+                  // then a 4-lane shuffle reduction over the k quarters
+                  constexpr int OUTS = 8;
+                  const int kq = f & 3, rp = (f >> 2) & 15, og = f >> 6;
+                  const uint32_t vrow = vt_a + (2 * rp) * kFTU * 4;
+                  const uint32_t wrow = sp_a + (kSmLastW - C::kSmShift + og * OUTS * kFTU) * 4;
+                  const int osw = (og * OUTS) >> 2;  // (o >> 2) = osw + (oo >> 2)
+#pragma unroll
+                  for (int ps = 0; ps < ER / 32; ++ps) {
+                    // [32][128] fp32; float4 slot j4 of row r sits at (j4 & ~7) | ((j4 ^ (j4 >> 3) ^ ((r >> 1) << 2)) & 7): the 8
+                    // lanes of a quarter warp of the reader (4 k-quarters x 2 row pairs) then hit 8 different bank groups
+#pragma unroll
+                    for (int r = 0; r < 32; ++r)
+                      sts32(vt_a + (r * kFTU + (((((f >> 2) & ~7) | (((f >> 2) ^ (f >> 5) ^ ((r >> 1) << 2)) & 7)) << 2) | (f & 3))) * 4,
+                            v[ps * 32 + r]);
+                    bar_group(h);
+                    float po[2][OUTS];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                      for (int oo = 0; oo < OUTS; ++oo) po[q][oo] = 0.f;
+#pragma unroll 2
+                    for (int jj = 0; jj < 8; ++jj) {
+                      const int slot_ = (kq << 3) | ((jj ^ kq ^ (rp << 2)) & 7);  // both rows of the pair share (row >> 1)
+                      // all loads of the step first, then the FMAs (see the first layer)
+                      float4 w[OUTS];
+                      const float4 x0 = lds128(vrow + (slot_ << 4));
+                      const float4 x1 = lds128(vrow + kFTU * 4 + (slot_ << 4));
+#pragma unroll
+                      for (int oo = 0; oo < OUTS; ++oo)
+                        w[oo] = lds128(wrow + (oo * kFTU + (((kq << 3) | ((jj ^ kq ^ (osw + (oo >> 2))) & 7)) << 2)) * 4);
+#pragma unroll
+                      for (int oo = 0; oo < OUTS; ++oo) {
+                        po[0][oo] = fmaf(x0.x, w[oo].x, po[0][oo]);
+                        po[1][oo] = fmaf(x1.x, w[oo].x, po[1][oo]);
+                        po[0][oo] = fmaf(x0.y, w[oo].y, po[0][oo]);
+                        po[1][oo] = fmaf(x1.y, w[oo].y, po[1][oo]);
+                        po[0][oo] = fmaf(x0.z, w[oo].z, po[0][oo]);
+                        po[1][oo] = fmaf(x1.z, w[oo].z, po[1][oo]);
+                        po[0][oo] = fmaf(x0.w, w[oo].w, po[0][oo]);
+                        po[1][oo] = fmaf(x1.w, w[oo].w, po[1][oo]);
+                      }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                      for (int oo = 0; oo < OUTS; ++oo) {
+                        float x = po[q][oo];
+                        x += __shfl_xor_sync(0xffffffffu, x, 1);
+                        x += __shfl_xor_sync(0xffffffffu, x, 2);
+                        po[q][oo] = x;
+                      }
+                    // all four lanes of a k-quarter group hold the sums: lane kq publishes outputs og*8 + 2kq, +1 of both rows,
+                    // straight from its registers, in the LL format
+                    if (og * 4 + kq < n_units) {
+#pragma unroll
+                      for (int q = 0; q < 2; ++q) {
+                        const float v0 = kq == 0 ? po[q][0] : kq == 1 ? po[q][2] : kq == 2 ? po[q][4] : po[q][6];
+                        const float v1 = kq == 0 ? po[q][1] : kq == 1 ? po[q][3] : kq == 2 ? po[q][5] : po[q][7];
+                        st_ll(part_slot + (((size_t)pb * NT + t) * XR + xrow0 + row0 + ps * 32 + 2 * rp + q) * kPartRowBytes + (og * 4 + kq) * 16,
+                              v0, v1, pexp);
+                      }
+                    }
+                    if (ps + 1 < ER / 32 || pass + 1 < C::kPasses) bar_group(h);  // the tile is free for the next 32 rows
+                  }
                 }
               }
+            }
+            if (l > 0) ++layers;
+            if (l < p.n_big) {
               if (F16 && pub_max > 65504.f) report_range(p.status, p.status_host);  // the fp16 head of such a value is inf
               if constexpr (JIT) fence_proxy_async_smem();  // the tensor core reads the own chunks through the async proxy
-              bar_epi<ET>();
+              bar_dom();
               if constexpr (JIT) {
                 if (tid == 0) {
                   mbar_arrive(&sm.full[0]);
@@ -1323,88 +1464,20 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
               }
               // st.release is cumulative over the stores the barrier ordered before it.  It is NOT optional: a relaxed
               // flag store lets consumers read stale chunks (scripts/stress_flow.py); its MEMBAR.GPU costs ~1 us.
-              if (tid == 0) {
-                trace_ev(p, g * 4 + l, 4);
+              if (dt == 0) {  // (ping-pong: thread 0 of the group)
+                if (tid == 0) trace_ev(p, g * 4 + l, 4);
                 st_release(aflag + (buf * NT + t) * FW + (KS ? kh : 0), p.epoch + 1 + act_w[buf]);
-                trace_ev(p, g * 4 + l, 5);
+                if (tid == 0) trace_ev(p, g * 4 + l, 5);
               }
               ++act_w[buf];
               ++axchg;
               if (tid == 0) trace_ev(p, g * 4 + l, 10);
-            }
-          }
-
-          // ---- last layer: fp32, through a transposed copy of the activations; every group works on its own rows, 32 at a
-          //      time ----
-          if (tid == 0) trace_ev(p, g * 4 + 3, 11);
-          const int pb = pxchg & 1;
-          const uint32_t pexp = p.epoch + 1 + part_w[pb];  // sequence number of this exchange
-          const int n_units = tg_len;                       // 2 * tg_len outputs, two per 16-byte unit
-          {
-            // thread = (k quarter kq, row pair rp, output group og): 2 rows x 8 outputs over 32 of the 128 features,
-            // then a 4-lane shuffle reduction over the k quarters
-            constexpr int OUTS = 8;
-            const int kq = f & 3, rp = (f >> 2) & 15, og = f >> 6;
-            const uint32_t vrow = vt_a + (2 * rp) * kFTU * 4;
-            const uint32_t wrow = sp_a + (kSmLastW - C::kSmShift + og * OUTS * kFTU) * 4;
-            const int osw = (og * OUTS) >> 2;  // (o >> 2) = osw + (oo >> 2)
-#pragma unroll
-            for (int ps = 0; ps < ER / 32; ++ps) {
-              // [32][128] fp32; float4 slot j4 of row r sits at (j4 & ~7) | ((j4 ^ (j4 >> 3) ^ ((r >> 1) << 2)) & 7): the 8
-              // lanes of a quarter warp of the reader (4 k-quarters x 2 row pairs) then hit 8 different bank groups
-#pragma unroll
-              for (int r = 0; r < 32; ++r)
-                sts32(vt_a + (r * kFTU + (((((f >> 2) & ~7) | (((f >> 2) ^ (f >> 5) ^ ((r >> 1) << 2)) & 7)) << 2) | (f & 3))) * 4,
-                      v[ps * 32 + r]);
-              bar_group(h);
-              float po[2][OUTS];
-#pragma unroll
-              for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int oo = 0; oo < OUTS; ++oo) po[q][oo] = 0.f;
-#pragma unroll 2
-              for (int jj = 0; jj < 8; ++jj) {
-                const int slot_ = (kq << 3) | ((jj ^ kq ^ (rp << 2)) & 7);  // both rows of the pair share (row >> 1)
-                // all loads of the step first, then the FMAs (see the first layer)
-                float4 w[OUTS];
-                const float4 x0 = lds128(vrow + (slot_ << 4));
-                const float4 x1 = lds128(vrow + kFTU * 4 + (slot_ << 4));
-#pragma unroll
-                for (int oo = 0; oo < OUTS; ++oo)
-                  w[oo] = lds128(wrow + (oo * kFTU + (((kq << 3) | ((jj ^ kq ^ (osw + (oo >> 2))) & 7)) << 2)) * 4);
-#pragma unroll
-                for (int oo = 0; oo < OUTS; ++oo) {
-                  po[0][oo] = fmaf(x0.x, w[oo].x, po[0][oo]);
-                  po[1][oo] = fmaf(x1.x, w[oo].x, po[1][oo]);
-                  po[0][oo] = fmaf(x0.y, w[oo].y, po[0][oo]);
-                  po[1][oo] = fmaf(x1.y, w[oo].y, po[1][oo]);
-                  po[0][oo] = fmaf(x0.z, w[oo].z, po[0][oo]);
-                  po[1][oo] = fmaf(x1.z, w[oo].z, po[1][oo]);
-                  po[0][oo] = fmaf(x0.w, w[oo].w, po[0][oo]);
-                  po[1][oo] = fmaf(x1.w, w[oo].w, po[1][oo]);
-                }
+            } else if constexpr (PP) {
+              bar_dom();
+              if (dt == 0) {
+                __threadfence_block();
+                atomicExch(&sm.vt_lock, 0);
               }
-#pragma unroll
-              for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int oo = 0; oo < OUTS; ++oo) {
-                  float x = po[q][oo];
-                  x += __shfl_xor_sync(0xffffffffu, x, 1);
-                  x += __shfl_xor_sync(0xffffffffu, x, 2);
-                  po[q][oo] = x;
-                }
-              // all four lanes of a k-quarter group hold the sums: lane kq publishes outputs og*8 + 2kq, +1 of both rows,
-              // straight from its registers, in the LL format
-              if (og * 4 + kq < n_units) {
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                  const float v0 = kq == 0 ? po[q][0] : kq == 1 ? po[q][2] : kq == 2 ? po[q][4] : po[q][6];
-                  const float v1 = kq == 0 ? po[q][1] : kq == 1 ? po[q][3] : kq == 2 ? po[q][5] : po[q][7];
-                  st_ll(part_slot + (((size_t)pb * NT + t) * XR + xrow0 + row0 + ps * 32 + 2 * rp + q) * kPartRowBytes + (og * 4 + kq) * 16,
-                        v0, v1, pexp);
-                }
-              }
-              if (ps + 1 < ER / 32) bar_group(h);  // the tile is free for the next 32 rows
             }
           }
           if (tid == 0) {
@@ -1412,7 +1485,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
             trace_ev(p, g * 4 + 3, 15);
           }
           // ---- sum the team's partial sums in a fixed order (bitwise identical replicas), polling the data itself ----
-          for (int i = tid; i < RT * 4; i += ET) {
+          for (int i = dt; i < RT * 4; i += DT) {
             const int r = i >> 2, o4 = i & 3;
             float4 acc = lds128(sp_a + (kSmLastB - C::kSmShift + 4 * o4) * 4);
             const uint8_t* src = part_slot + ((size_t)pb * NT * XR + xrow0 + r) * kPartRowBytes + (2 * o4) * 16;
@@ -1458,28 +1531,28 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
                 acc.w += __uint_as_float(x1[c].z);
               }
             }
-            sts128(smem_u32(&sm.a[r][4 * o4]), acc);
+            sts128(smem_u32(&sa[r][4 * o4]), acc);
           }
           if (tid == 0) trace_ev(p, g * 4 + 3, 12);
           __syncwarp();
           if (lane == 0) mbar_arrive(&sm.small_empty[sb]);
           ++part_w[pb];
           ++pxchg;
-          bar_epi<ET>();
-          for (int i = tid; i < RT * tg_len; i += ET) {
+          bar_dom();
+          for (int i = dt; i < RT * tg_len; i += DT) {
             const int r = i / tg_len, j = i % tg_len;
-            const float sc = p.clamp_scale * atanf(sm.a[r][j]);
-            const float tr = sm.a[r][tg_len + j];
-            float& uu = sm.u[r][ph[tg_off + j]];
+            const float sc = p.clamp_scale * atanf(sa[r][j]);
+            const float tr = sa[r][tg_len + j];
+            float& uu = su[r][ph[tg_off + j]];
             uu = p.forward ? fmaf(uu, expf(sc), tr) : (uu - tr) * expf(-sc);
           }
           if (p.forward)  // log-det of the block: sum of the (clamped) scales, one thread per row, fixed order
-            for (int r = tid; r < RT; r += ET) {
-              float acc = sm.logdet[r];
-              for (int j = 0; j < tg_len; ++j) acc += p.clamp_scale * atanf(sm.a[r][j]);
-              sm.logdet[r] = acc;
+            for (int r = dt; r < RT; r += DT) {
+              float acc = sld[r];
+              for (int j = 0; j < tg_len; ++j) acc += p.clamp_scale * atanf(sa[r][j]);
+              sld[r] = acc;
             }
-          bar_epi<ET>();
+          bar_dom();
           if (tid == 0) trace_ev(p, g * 4 + 3, 13);
         }
         if (!p.forward && !p.fold) permute_state(p.perm_inv + blk * kPad);
@@ -1487,19 +1560,19 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
 
       if (t == 0) {
         const uint8_t* phf = sm.phys[p.fold ? n_blocks : 0];  // where the logical columns sit at the end
-        for (int i = tid; i < RT * p.out_cols; i += ET) {
+        for (int i = dt; i < RT * p.out_cols; i += DT) {
           const int r = i / p.out_cols, j = i % p.out_cols;
           const int row = rg * XR + xrow0 + r;
           if (row >= p.batch) continue;
           float o;
           if (p.finalize) {
             o = 0.f;
-            for (int k = 0; k < p.W; ++k) o = fmaf(sm.u[r][phf[k]] - p.flt_b[k], p.m_inv[k * kPad + j], o);
+            for (int k = 0; k < p.W; ++k) o = fmaf(su[r][phf[k]] - p.flt_b[k], p.m_inv[k * kPad + j], o);
             // NaN / inf are reported BEFORE the clamp, and NaN survives it as in torch.clamp (robot.clamp_to_joint_limits)
             if (!isfinite(o)) report_nonfinite(p.status, p.status_host);
             if (p.clamp_out && j < p.ndof && o == o) o = fminf(fmaxf(o, p.lo[j]), p.hi[j]);
           } else {
-            o = sm.u[r][phf[j]];
+            o = su[r][phf[j]];
             if (!isfinite(o)) report_nonfinite(p.status, p.status_host);
           }
           p.out[(size_t)row * p.out_ld + j] = o;
@@ -1507,10 +1580,10 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS>::kThreads, 1) flow_inverse_um
           for (int r = 0; r < p.n_peers; ++r) p.peer_out[r][(size_t)(p.peer_row0 + row) * p.peer_ld + j] = o;
         }
         if (p.forward && p.logdet_out != nullptr)
-          for (int r = tid; r < RT; r += ET)
-            if (rg * XR + xrow0 + r < p.batch) p.logdet_out[rg * XR + xrow0 + r] = sm.logdet[r];
+          for (int r = dt; r < RT; r += DT)
+            if (rg * XR + xrow0 + r < p.batch) p.logdet_out[rg * XR + xrow0 + r] = sld[r];
       }
-      bar_epi<ET>();
+      bar_dom();
     }
   }
 
