@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
       const uint8_t* wnext =
           reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n2 * p.n_big + l2) * NT + t) * KCH * kWChunkU;
       for (int k = lane; k < KCH; k += 32)
-        if (k % p.slots == slot) bulk_prefetch_l2(wnext + (size_t)k * kWChunkU, kWChunkU);
+        if (k % p.slots == slot && (!KS || k / KCHL == kh)) bulk_prefetch_l2(wnext + (size_t)k * kWChunkU, kWChunkU);  // (k-split: own half only)
     };
     if constexpr (!JIT) {
       // ===== split rings (see Cfg::kSplit): loader warp 0 streams the weights, loader warp 1 the exchanged activations;

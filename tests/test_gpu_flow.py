@@ -518,7 +518,9 @@ def test_nan_inputs_propagate_like_torch_clamp_and_are_reported():
 def test_last_kernel_reports_what_was_launched():
     solver, hp, sd = _solver(12, 7, 3, 1024)
     latent, poses, cond = _inputs(2048, 7)
-    for batch, tag in ((512, "<32,false,true,ksplit>"), (1024, "<64,false,true>"), (2048, "<128,false,true>")):  # <rows per CTA, just-in-time first layer, fp16x3>
+    latent, poses, cond = _inputs(2400, 7)
+    # <rows per CTA (per group), just-in-time first layer, fp16x3, variant>
+    for batch, tag in ((512, "<32,false,true,ksplit>"), (1024, "<64,false,true>"), (2048, "<128,false,true>"), (2400, "<128,false,true,pingpong>")):
         solver.nn_model.inverse(latent[:batch].to(DEV), cond[:batch].to(DEV))
         assert solver.nn_model.last_kernel().endswith("flow_inverse_umma_kernel" + tag), solver.nn_model.last_kernel()
 
@@ -597,3 +599,48 @@ def test_ksplit_kernel_other_shapes_and_directions():
     tiled = psolver.nn_model.inverse(lat.to(DEV), pos[:32].to(DEV))
     assert (tiled.cpu() - _oracle(psd, php, lat, cnd[:32].repeat(3, 1))).abs().max() < TOL
     assert psolver.nn_model.status() == 0 and solver.nn_model.status() == 0
+
+
+# ---- ping-pong (Cfg::PP): two independent 128-row groups per CTA; the kernel of every batch beyond one wave of 128-row groups ----
+@pytest.mark.parametrize("precision", ["fp16x3", "bf16x3"])
+@pytest.mark.parametrize("batch", [2305, 3000, 4737])
+def test_pingpong_kernel_matches_oracle_and_the_single_group_kernel(batch, precision, monkeypatch):
+    """Same layer arithmetic as the 128-row single-group kernel (bf16x3: bit for bit; fp16x3: one accumulator tile instead
+    of two), the groups of a CTA out of phase.  Odd numbers of row groups (2305 -> 19, 4737 -> 38 = 2 full rounds + 2) walk
+    empty groups."""
+    model, hp, sd = _model_with_precision(precision)
+    latent, poses, cond = _inputs(batch, 7)
+    out = model.inverse(latent.to(DEV), cond.to(DEV))
+    assert "pingpong" in model.last_kernel(), model.last_kernel()
+    idx = torch.arange(0, batch, 7)  # every 7th row keeps the CPU oracle at seconds; rows are independent
+    idx = torch.cat([idx, torch.arange(batch - 130, batch)])  # ... and the ragged tail
+    assert (out.cpu()[idx] - _oracle(sd, hp, latent[idx], cond[idx])).abs().max() < (4e-5 if precision == "fp16x3" else TOL)  # (fp16x3 on ONE accumulator tile: 2.7e-5 measured)
+    for _ in range(10):
+        assert torch.equal(model.inverse(latent.to(DEV), cond.to(DEV)), out)
+    assert model.status() == 0
+    monkeypatch.setenv("IKFLOW_B200_PP", "0")
+    plain, _, _ = _model_with_precision(precision)
+    ref = plain.inverse(latent.to(DEV), cond.to(DEV))
+    assert "pingpong" not in plain.last_kernel() and "<128," in plain.last_kernel()
+    if precision == "bf16x3":
+        assert torch.equal(ref, out)
+    else:
+        assert (ref - out).abs().max() < 2e-5
+
+
+def test_pingpong_kernel_forward_pass_and_block_ranges():
+    solver, hp, sd = _solver(3, 7, 3, 1024)
+    batch = 2500
+    latent, poses, cond = _inputs(batch, 7)
+    x = (torch.rand(batch, 7, generator=torch.Generator().manual_seed(3)) * 2 - 1) * 2.0
+    z, logdet = solver.nn_model(x.to(DEV), c=cond.to(DEV), rev=False)
+    assert "pingpong" in solver.nn_model.last_kernel()
+    z_ref, ld_ref = freia_flow.flow_forward(sd, x, cond, hp.nb_nodes, hp.coeff_fn_config, hp.rnvp_clamp)
+    assert (z.cpu() - z_ref).abs().max() < TOL * max(1.0, float(z_ref.abs().max())) and (logdet.cpu() - ld_ref).abs().max() < 1e-3
+    back, _ = solver.nn_model(z, c=cond.to(DEV), rev=True)
+    assert (back.cpu() - x).abs().max() < 1e-3
+    _, _, inter = freia_flow.flow_inverse(sd, latent, cond, 3, 3, 2.5, return_intermediates=True)
+    part = solver.nn_model.inverse_blocks(latent.to(DEV), cond.to(DEV), 2, 1)
+    assert "pingpong" in solver.nn_model.last_kernel()
+    assert (part.cpu() - inter[1]).abs().max() < TOL
+    assert solver.nn_model.status() == 0
