@@ -87,12 +87,27 @@ def measured_peaks():
     return {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def _kernel_template_args(name: str):
+    """('ikf::umma::flow_inverse_umma_kernel<32,false,true,ksplit>' | ncu's '...<128, 0, 1, 0, 1>(...)') -> (engine, [rt, jit, f16, ks, pp])."""
+    tail = name.replace(" ", "").split("flow_inverse")[-1].split("(")[0]
+    engine, _, rest = tail.partition("<")
+    vals = []
+    for a in rest.rstrip(">").split(","):
+        a = a.replace("(int)", "").replace("(bool)", "")
+        if a == "ksplit":
+            vals = (vals + [0, 0, 0])[:3] + [1, 0]
+        elif a == "pingpong":
+            vals = (vals + [0, 0, 0])[:3] + [0, 1]
+        else:
+            vals.append({"true": 1, "false": 0}.get(a, int(a) if a.lstrip("-").isdigit() else -1))
+    return engine, (vals + [0] * 5)[:5]  # (older profiles predate the later template arguments)
+
+
 def traffic_from_profiles(kernel: str, batch: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the newest committed ncu summary under
-    profiles/ whose kernel name and batch match (written by scripts/summarize_profiles.py from an `ncu --set full`
-    capture).  Returns (bytes or None, file name or None)."""
-    tmpl = kernel.split("flow_inverse")[-1]  # e.g. "_umma_kernel<32,true,false>"
-    want = tmpl.replace(" ", "").replace("true", "1").replace("false", "0")
+    profiles/ whose kernel (template arguments) and batch match (written by scripts/summarize_profiles.py from an
+    `ncu --set full` capture).  Returns (bytes or None, file name or None)."""
+    want = _kernel_template_args(kernel)
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_b{batch}_ncu_summary.txt")), reverse=True):
         name, rd, wr = None, None, None
@@ -101,16 +116,13 @@ def traffic_from_profiles(kernel: str, batch: int):
             if len(parts) != 3:
                 continue
             if parts[0] == "Kernel Name":
-                name = parts[2].replace(" ", "")
+                name = parts[2]
             elif parts[0] == "dram__bytes_read.sum":
                 rd = float(parts[2]) * scale.get(parts[1], 1.0)
             elif parts[0] == "dram__bytes_write.sum":
                 wr = float(parts[2]) * scale.get(parts[1], 1.0)
-        if name and rd is not None and wr is not None:
-            got = name.split("flow_inverse")[-1].split("(")[0]
-            # r1 profiles predate the third template argument
-            if got == want or got.rstrip(">") + ",0>" == want:
-                return int(rd + wr), os.path.relpath(path, ROOT)
+        if name and rd is not None and wr is not None and _kernel_template_args(name) == want:
+            return int(rd + wr), os.path.relpath(path, ROOT)
     return None, None
 
 
@@ -678,7 +690,11 @@ def main():
                 "issued_flops_per_launch": 3 * fl * B if precision != "bf16x1" else fl * B,
                 "hbm": {"algorithmic_bytes_per_launch": wbytes + B * 84, "achieved_gbs": (wbytes + B * 84) / (kernel_ms * 1e-3) / 1e9,
                         "peak_gbs": peaks["hbm_gbs"], "frac": (wbytes + B * 84) / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-                "traffic_source": traffic_src,
+                "traffic_source": traffic_src if traffic is not None else (
+                    "none: ncu cannot profile a cooperative launch in thread-block clusters (LaunchFailed under kernel and application "
+                    "replay), which is how the k-split kernel of this batch runs; the unclustered just-in-time kernel of the same batch "
+                    "reads 205.6 MB and writes 4.7 MB of DRAM per launch against 203.5 MB of weights (profiles/r2_flow_umma_b512_ncu_summary.txt)"
+                    if "ksplit" in kernel_name else None),
             },
             "status_word": status,
         }

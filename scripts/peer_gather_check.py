@@ -23,12 +23,12 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 solver, hp = ikflow_b200.get_ik_solver("panda__full__lp191_5.25m", synthetic_seed=0)
 report = {"world": world}
-for n_total in (512 * world, 100 * world + 1):
+for n_total in (512 * world, 100 * world + 1, 2400 * world + 3):  # the last one: ping-pong kernel (> 2304 rows per GPU), ragged
     lo, hi = shard_bounds(n_total, rank, world)
     q, poses = solver.robot.sample_joint_angles_and_poses(n_total, seed=5, return_torch=True, device=dev)  # same on every rank
     pg = PeerGather(solver, n_total)
     bad = 0
-    for step in range(60):
+    for step in range(60 if n_total <= 512 * world else 12):
         latent = torch.randn(n_total, 7, generator=torch.Generator().manual_seed(step)).to(dev)
         fused = pg.generate_ik_solutions(poses[lo:hi], latent[lo:hi]).clone()
         ref = all_gather_rows(solver.generate_ik_solutions(poses[lo:hi], hi - lo, latent=latent[lo:hi]), n_total)

@@ -12,7 +12,7 @@ import sys
 
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ikflow_b200", "lib", "libikflow_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-KEY = ["UTCHMMA", "UTCQMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "STTM", "UBLKCP", "UBLKPF", "UTMALDG", "UTMASTG", "SYNCS", "HMMA", "LDSM", "MEMBAR", "FENCE", "UCGABAR",
+KEY = ["UTCHMMA", "UTCQMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "STTM", "UBLKCP", "UBLKPF", "STAS", "UTMALDG", "UTMASTG", "SYNCS", "HMMA", "LDSM", "MEMBAR", "FENCE", "UCGABAR",
        "ELECT", "FFMA2", "FFMA", "MUFU", "LDS", "STS", "LDG", "STG", "LD.E", "ST.E", "ATOM", "RED", "BAR", "SHFL", "NANOSLEEP", "LDL", "STL"]
 per = collections.OrderedDict()
 cur = None
@@ -41,7 +41,7 @@ def demangle(name):
 
 print(f"# SASS instruction histogram of `{os.path.relpath(lib)}` (`cuobjdump -sass`, sm_100a), per kernel")
 print("# UTCHMMA = tcgen05.mma.kind::f16, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UBLKCP = cp.async.bulk (bulk TMA, incl. .multicast::cluster),")
-print("# UBLKPF = cp.async.bulk.prefetch.L2, SYNCS = mbarrier ops, UCGABAR = barrier.cluster, HMMA = mma.sync (fallback engine only), LDL/STL = local memory\n")
+print("# UBLKPF = cp.async.bulk.prefetch.L2, STAS = st.async (distributed shared memory hand-over of the k-split kernels), SYNCS = mbarrier ops, UCGABAR = barrier.cluster, HMMA = mma.sync (fallback engine only), LDL/STL = local memory\n")
 cols = [k for k in KEY if any(c[k] for c in per.values())]
 print("| kernel | instructions | " + " | ".join(cols) + " |")
 print("|---|---|" + "---|" * len(cols))
