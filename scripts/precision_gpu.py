@@ -36,5 +36,5 @@ for stress in (1.0, 1.5, 2.0, 3.0):
         model.load_state_dict(sd)
         out = model.inverse(latent.cuda(), cond.cuda()).cpu()
         e64, e32 = (out.double() - ref64).abs(), (out - ref32).abs()
-        print(f"   {precision:7s} vs fp64: abs {e64.max():.3e} rel {(e64 / den).max():.3e}   vs fp32 CPU: abs {e32.max():.3e} rel {(e32 / (1 + ref32.abs())).max():.3e}   status {model.status()}")
+        print(f"   {precision:7s} vs fp64: abs {e64.max():.3e} rel {(e64 / den).max():.3e}   vs fp32 CPU: abs {e32.max():.3e} rel {(e32 / (1 + ref32.abs())).max():.3e}   status {model.status()}  {model.last_kernel().split('kernel')[-1]}")
         del model
