@@ -132,7 +132,7 @@ struct IkfFlow {
     size_t smem = 0;
     const char* name = "";
     int max_slots_cs[5] = {0, 0, 0, 0, 0};  // [cs]: team slots that are co-resident when launched in clusters of cs CTAs (cs = 2, 4)
-  } kern[6];  // [4]: k-split pairs (64-row groups shared by two CTAs per feature tile), [5]: ping-pong (two 128-row groups per CTA); tcgen05 only
+  } kern[8];  // [7]: ping-pong with two 32-row groups; [4]: k-split pairs (64-row groups shared by two CTAs per feature tile), [5] / [6]: ping-pong (two 128- / 64-row groups per CTA); tcgen05 only
   // tcgen05 engine: CTAs per cluster for the weight multicast across teams (1 = off); IKFLOW_B200_CLUSTER overrides
   // fused gather (ikf_flow_set_peers): peer-mapped gathered buffers / flag arrays of every rank of the node
   int n_ranks = 0, rank = 0;
@@ -457,6 +457,8 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
     f->kern[3] = {(const void*)umma::flow_inverse_umma_kernel<32, true, true>, umma::Cfg<32, true>::kThreads, f->smem32j, "ikf::umma::flow_inverse_umma_kernel<32,true,true>"};
     f->kern[4] = {(const void*)umma::flow_inverse_umma_kernel<32, false, true, true>, umma::Cfg<32, false, true>::kThreads, sizeof(umma::Smem<32, false, true>) + 1024, "ikf::umma::flow_inverse_umma_kernel<32,false,true,ksplit>"};
     f->kern[5] = {(const void*)umma::flow_inverse_umma_kernel<128, false, true, false, true>, umma::Cfg<128, false, false, true>::kThreads, sizeof(umma::Smem<128, false, false, true>) + 1024, "ikf::umma::flow_inverse_umma_kernel<128,false,true,pingpong>"};
+    f->kern[6] = {(const void*)umma::flow_inverse_umma_kernel<64, false, true, false, true>, umma::Cfg<64, false, false, true>::kThreads, sizeof(umma::Smem<64, false, false, true>) + 1024, "ikf::umma::flow_inverse_umma_kernel<64,false,true,pingpong>"};
+    f->kern[7] = {(const void*)umma::flow_inverse_umma_kernel<32, false, true, false, true>, umma::Cfg<32, false, false, true>::kThreads, sizeof(umma::Smem<32, false, false, true>) + 1024, "ikf::umma::flow_inverse_umma_kernel<32,false,true,pingpong>"};
   } else if (engine) {
     f->kern[0] = {(const void*)umma::flow_inverse_umma_kernel<32>, umma::Cfg<32>::kThreads, f->smem32, "ikf::umma::flow_inverse_umma_kernel<32,false,false>"};
     f->kern[1] = {(const void*)umma::flow_inverse_umma_kernel<64>, umma::Cfg<64>::kThreads, f->smem64, "ikf::umma::flow_inverse_umma_kernel<64,false,false>"};
@@ -464,6 +466,8 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
     f->kern[3] = {(const void*)umma::flow_inverse_umma_kernel<32, true>, umma::Cfg<32, true>::kThreads, f->smem32j, "ikf::umma::flow_inverse_umma_kernel<32,true,false>"};
     f->kern[4] = {(const void*)umma::flow_inverse_umma_kernel<32, false, false, true>, umma::Cfg<32, false, true>::kThreads, sizeof(umma::Smem<32, false, true>) + 1024, "ikf::umma::flow_inverse_umma_kernel<32,false,false,ksplit>"};
     f->kern[5] = {(const void*)umma::flow_inverse_umma_kernel<128, false, false, false, true>, umma::Cfg<128, false, false, true>::kThreads, sizeof(umma::Smem<128, false, false, true>) + 1024, "ikf::umma::flow_inverse_umma_kernel<128,false,false,pingpong>"};
+    f->kern[6] = {(const void*)umma::flow_inverse_umma_kernel<64, false, false, false, true>, umma::Cfg<64, false, false, true>::kThreads, sizeof(umma::Smem<64, false, false, true>) + 1024, "ikf::umma::flow_inverse_umma_kernel<64,false,false,pingpong>"};
+    f->kern[7] = {(const void*)umma::flow_inverse_umma_kernel<32, false, false, false, true>, umma::Cfg<32, false, false, true>::kThreads, sizeof(umma::Smem<32, false, false, true>) + 1024, "ikf::umma::flow_inverse_umma_kernel<32,false,false,pingpong>"};
   } else {
     f->kern[0] = {(const void*)flow_inverse_kernel<32>, kThreads, f->smem32, "ikf::flow_inverse_kernel<32>"};
     f->kern[1] = {(const void*)flow_inverse_kernel<64>, kThreads, f->smem64, "ikf::flow_inverse_kernel<64>"};
@@ -473,6 +477,10 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   if (!f->ksplit || KCH % 4 != 0 || NT > 16) f->kern[4] = IkfFlow::Kernel();  // (flag bits: 2 NT <= 32; whole chunk pairs per half)
   if (const char* env = std::getenv("IKFLOW_B200_PP")) f->pingpong = std::atoi(env) != 0;
   if (!f->pingpong || f->kern[5].smem > (size_t)prop.sharedMemPerBlockOptin) f->kern[5] = IkfFlow::Kernel();
+  if (!f->pingpong || f->kern[6].smem > (size_t)prop.sharedMemPerBlockOptin) f->kern[6] = IkfFlow::Kernel();
+  if (const char* env = std::getenv("IKFLOW_B200_PP64")) { if (std::atoi(env) == 0) f->kern[6] = IkfFlow::Kernel(); }
+  if (!f->pingpong || f->kern[7].smem > (size_t)prop.sharedMemPerBlockOptin) f->kern[7] = IkfFlow::Kernel();
+  if (const char* env = std::getenv("IKFLOW_B200_PP32")) { if (std::atoi(env) == 0) f->kern[7] = IkfFlow::Kernel(); }
   {
     // the teams spin on each other's flags, so every CTA of a launch must be resident: size the slot count from
     // what the device really fits
@@ -663,13 +671,29 @@ static int flow_launch_locked(IkfFlow* flow, const float* in, int in_ld, const f
     p.n_rowgroups = (batch + 127) / 128;
     p.slots = std::min((p.n_rowgroups + 1) / 2, flow->slots_max);  // teams; each runs the exchange slots 2 s, 2 s + 1
   }
-  const IkfFlow::Kernel& k = flow->kern[pp ? 5 : ks ? 4 : (rt == 32 && flow->jit) ? 3 : rt == 32 ? 0 : rt == 64 ? 1 : 2];
+  // ... and two 64-row groups per CTA where the single-group kernel would run one wave of 128-row groups (1152 < B <= 2304)
+  const bool pp64 = flow->engine && flow->kern[6].fn && !flow->forced_rt && !ks && !pp && (batch + 63) / 64 > flow->slots_max &&
+                    (batch + 127) / 128 <= flow->slots_max;
+  if (pp64) {
+    rt = 64;
+    p.n_rowgroups = (batch + 63) / 64;
+    p.slots = std::min((p.n_rowgroups + 1) / 2, flow->slots_max);
+  }
+  // ... and two 32-row groups per CTA where the single-group kernel would run one wave of 64-row groups (576 < B <= 1152)
+  const bool pp32 = flow->engine && flow->kern[7].fn && !flow->forced_rt && !ks && !pp && !pp64 && (batch + 31) / 32 > flow->slots_max &&
+                    (batch + 63) / 64 <= flow->slots_max;
+  if (pp32) {
+    rt = 32;
+    p.n_rowgroups = (batch + 31) / 32;
+    p.slots = std::min((p.n_rowgroups + 1) / 2, flow->slots_max);
+  }
+  const IkfFlow::Kernel& k = flow->kern[pp ? 5 : pp64 ? 6 : pp32 ? 7 : ks ? 4 : (rt == 32 && flow->jit) ? 3 : rt == 32 ? 0 : rt == 64 ? 1 : 2];
   // Clusters of cs CTAs = the CTAs with the same feature tile of cs neighbouring teams share every weight chunk by
   // multicast (FlowParams::cluster).  Needs cs teams at least; the slot count becomes a multiple of cs (surplus teams
   // walk empty row groups).
   int cs = 1;
   if (ks) cs = 2;  // (the pair is the cluster; no weight multicast: its CTAs multiply different k-chunks)
-  else if (pp) cs = 1;
+  else if (pp || pp64 || pp32) cs = 1;
   else if (flow->engine && flow->cluster_ok)
     for (int c = (&k == &flow->kern[3]) ? flow->cluster_pref_jit : flow->cluster_pref; c > 1; c >>= 1)
       if (p.n_rowgroups >= c && k.max_slots_cs[c] >= c) {
@@ -698,7 +722,7 @@ static int flow_launch_locked(IkfFlow* flow, const float* in, int in_ld, const f
   p.trace_layers = flow->trace_layers;
   p.debug = flow->debug;
   // every flag of this launch stays below epoch + 1 + (row groups per slot) * (subnets) * (exchanges per subnet)
-  const uint32_t rg_per_slot = (uint32_t)((p.n_rowgroups + p.slots * (pp ? 2 : 1) - 1) / (p.slots * (pp ? 2 : 1)));
+  const uint32_t rg_per_slot = (uint32_t)((p.n_rowgroups + p.slots * ((pp || pp64 || pp32) ? 2 : 1) - 1) / (p.slots * ((pp || pp64 || pp32) ? 2 : 1)));
   flow->epoch += rg_per_slot * 2u * (uint32_t)(block_first - block_last + 1) * (uint32_t)(flow->n_big + 1) + 2u;
 
   const int grid = p.slots * flow->NT * (ks ? 2 : 1);

@@ -113,9 +113,9 @@ template <int RT, bool JIT = false, bool KS = false, bool PP = false>
 struct Cfg {
   static_assert(!JIT || RT == 32, "the just-in-time first layer is written for 32-row groups");
   static_assert(!KS || (RT == 32 && !JIT), "k-split pairs: 32 rows per CTA, exchanged first layer");
-  static_assert(!PP || (RT == 128 && !JIT && !KS), "ping-pong: two 128-row groups per CTA");
+  static_assert(!PP || (!JIT && !KS), "ping-pong: two row groups per CTA, exchanged first layer");
   static constexpr bool kPP = PP;
-  static constexpr int kPasses = PP ? 2 : 1;                  // passes of kEpiRows rows a group's warps make over its rows
+  static constexpr int kPasses = (PP && RT > 64) ? RT / 64 : 1;  // passes of kEpiRows rows a group's warps make over its rows
   static constexpr int kStateRows = PP ? 2 * RT : RT;         // rows of flow state held by the CTA
   static constexpr int kDomThreads = PP ? 128 : (RT > 64 ? 256 : 128);  // epilogue threads that synchronise with each other
   static constexpr int kXRows = KS ? 2 * RT : RT;     // rows of the exchanged activation tiles = rows of the MMA
@@ -129,8 +129,8 @@ struct Cfg {
   static constexpr uint32_t kFullCount = JIT ? 2 : 1;  // arrivals per phase of a stage's full barrier
   // Epilogue threads: 128 per group (thread = TMEM lane = hidden feature); a group drains EPI_ROWS accumulator columns.
   // RT = 128 uses two groups (rows 0-63 and 64-127) that work side by side.
-  static constexpr int kGroups = RT > 64 ? 2 : 1;
-  static constexpr int kEpiRows = RT / kGroups;
+  static constexpr int kGroups = (RT > 64 || PP) ? 2 : 1;
+  static constexpr int kEpiRows = PP ? (RT < 64 ? RT : 64) : RT / kGroups;
   static constexpr int kEpiWarps = 4 * kGroups;
   static constexpr int kEpiThreads = 32 * kEpiWarps;
   static constexpr int kStages = RT == 32 ? 4 : (RT == 64 ? 3 : 2);  // JIT kernel: stages of the unified ring
@@ -142,7 +142,7 @@ struct Cfg {
   // which is idle while it is needed (nothing is exchanged between the end of a subnet's second hidden layer and the
   // publication of the next subnet's first layer).
   static constexpr bool kSplit = !JIT;
-  static constexpr int kWStages = PP ? 2 : ((RT == 128 || KS) ? 3 : 4);
+  static constexpr int kWStages = PP ? (RT == 128 ? 2 : 3) : ((RT == 128 || KS) ? 3 : 4);
   static constexpr int kAStages = RT == 128 ? 2 : ((RT == 64 || KS) ? 3 : 4);
   static constexpr int kRecvBytes = KS ? 2 * RT * kFTU * 4 : 16;  // k-split: the peer's partial sums of this CTA's rows, 2 x [32][128] fp32
   // loader warp w owns the ring stages s with s % kLoaders == w: its waits on a stage's barriers are then strictly in
@@ -516,10 +516,10 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
   // them in fp32 round-to-nearest.
   // k-split: always two tiles, the first and the second half of the CTA's chunks (the first half is handed over to the peer
   // while the second is still being multiplied); 8 chunks per layer and CTA -> the same 16 steps per tile as above
-  constexpr int kAcc = KS ? 2 : (PP ? 1 : (F16 ? (XR == 128 ? 2 : 4) : 1));  // ping-pong: the second tile belongs to the other group
+  constexpr int kAcc = KS ? 2 : (PP ? (F16 ? (XR == 128 ? 1 : (XR == 64 ? 2 : 4)) : 1) : (F16 ? (XR == 128 ? 2 : 4) : 1));  // ping-pong: the other half of TMEM belongs to the other group
   constexpr int NG = PP ? 2 : 1;  // independent row groups per CTA
-  constexpr int kTmemColsK = PP ? 512 : kAcc * C::kAccCols <= 32 ? 32 : (kAcc * C::kAccCols <= 64 ? 64 : (kAcc * C::kAccCols <= 128 ? 128 : (kAcc * C::kAccCols <= 256 ? 256 : 512)));
-  static_assert(kAcc * C::kAccCols <= 512 && C::kMmaWarps == 1, "TMEM has 512 columns; the tiles are dealt by chunk index");
+  constexpr int kTmemColsK = PP ? (2 * kAcc * C::kAccCols <= 128 ? 128 : (2 * kAcc * C::kAccCols <= 256 ? 256 : 512)) : kAcc * C::kAccCols <= 32 ? 32 : (kAcc * C::kAccCols <= 64 ? 64 : (kAcc * C::kAccCols <= 128 ? 128 : (kAcc * C::kAccCols <= 256 ? 256 : 512)));
+  static_assert(NG * kAcc * C::kAccCols <= 512 && C::kMmaWarps == 1, "TMEM has 512 columns; the tiles are dealt by chunk index");
   extern __shared__ uint8_t smem_raw[];
   Smem<RT, JIT, KS, PP>& sm = *reinterpret_cast<Smem<RT, JIT, KS, PP>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -971,7 +971,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
                 // accumulator tile of this chunk (k-split: first / second half of the CTA's chunks)
                 const int tile = KS ? (i >= KCHL / 2 ? 1 : 0) : i % kAcc;
                 const bool accum = KS ? (i != 0 && i != KCHL / 2) : i >= kAcc;
-                const uint32_t tmem_u = tmem_u0 + (uint32_t)(tile * C::kAccCols) + (PP ? (uint32_t)(hh * C::kAccCols) : 0u);
+                const uint32_t tmem_u = tmem_u0 + (uint32_t)(tile * C::kAccCols) + (PP ? (uint32_t)(hh * kAcc * C::kAccCols) : 0u);
                 if (x3)
                   mma_chunk_x3(tmem_u, tmem_u + kCorrOff, idesc2, idesc, dwh, dwh + (uint64_t)(kWPlaneU >> 4), da, accum);
                 else
@@ -1042,7 +1042,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
     uint8_t* const part_slot = part_slot_of(gh);
     uint32_t* const aflag = aflag_of(gh);
     int row0 = PP ? 0 : h * ER;   // first row of the thread's current 64 (ping-pong: of the current pass)
-    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (PP ? (uint32_t)(h * C::kAccCols) : 0u);
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (PP ? (uint32_t)(h * kAcc * C::kAccCols) : 0u);
     uint32_t part_w[2] = {0, 0};
     uint32_t pxchg = 0;
     uint32_t act_w[2] = {0, 0};  // publishes so far into each activation scratch buffer
