@@ -139,7 +139,7 @@ struct IkfFlow {
   float* peer_out[ikf::kMaxPeers] = {};
   uint32_t* peer_flag[ikf::kMaxPeers] = {};
   uint32_t peer_seq = 0, peer_count_total = 0;
-  int cluster_pref = kDefaultCluster, cluster_pref_jit = kDefaultClusterJit;
+  int cluster_pref = kDefaultCluster, cluster_pref_jit = kDefaultClusterJit, cluster_pref_pp = 1;  // (IKFLOW_B200_CLUSTER_PP: ping-pong kernels)
   // k-split pairs for batches of up to ks_slots_max x 64 rows (IKFLOW_B200_KSPLIT=0|1 overrides the default)
   bool ksplit = kDefaultKSplit;
   int ks_slots_max = 0;
@@ -502,7 +502,11 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
     const int v = std::atoi(env);
     if (v == 1 || v == 2 || v == 4) f->cluster_pref = f->cluster_pref_jit = v;
   }
-  if (e == cudaSuccess && engine && (std::max(f->cluster_pref, f->cluster_pref_jit) > 1 || f->kern[4].fn)) {
+  if (const char* env = std::getenv("IKFLOW_B200_CLUSTER_PP")) {
+    const int v = std::atoi(env);
+    if (v == 1 || v == 2 || v == 4) f->cluster_pref_pp = v;
+  }
+  if (e == cudaSuccess && engine && (std::max(std::max(f->cluster_pref, f->cluster_pref_jit), f->cluster_pref_pp) > 1 || f->kern[4].fn)) {
     // how many clusters of cs CTAs the device holds at once (clusters are placed inside a GPC, so this is not num_sms / cs)
     for (IkfFlow::Kernel& k : f->kern) {
       if (!k.fn) continue;
@@ -693,14 +697,16 @@ static int flow_launch_locked(IkfFlow* flow, const float* in, int in_ld, const f
   // walk empty row groups).
   int cs = 1;
   if (ks) cs = 2;  // (the pair is the cluster; no weight multicast: its CTAs multiply different k-chunks)
-  else if (pp || pp64 || pp32) cs = 1;
-  else if (flow->engine && flow->cluster_ok)
-    for (int c = (&k == &flow->kern[3]) ? flow->cluster_pref_jit : flow->cluster_pref; c > 1; c >>= 1)
-      if (p.n_rowgroups >= c && k.max_slots_cs[c] >= c) {
+  else if (flow->engine && flow->cluster_ok) {
+    const bool anypp = pp || pp64 || pp32;
+    const int teams_wanted = anypp ? (p.n_rowgroups + 1) / 2 : p.n_rowgroups;  // (ping-pong: two row groups per team)
+    for (int c = (&k == &flow->kern[3]) ? flow->cluster_pref_jit : anypp ? flow->cluster_pref_pp : flow->cluster_pref; c > 1; c >>= 1)
+      if (teams_wanted >= c && k.max_slots_cs[c] >= c) {
         cs = c;
         break;
       }
-  if (cs > 1 && !ks) p.slots = std::min((p.n_rowgroups + cs - 1) / cs * cs, k.max_slots_cs[cs]);
+    if (cs > 1) p.slots = std::min((teams_wanted + cs - 1) / cs * cs, k.max_slots_cs[cs]);
+  }
   p.cluster = cs;
   p.ksplit = ks ? 1 : 0;
   p.n_peers = 0;
@@ -764,26 +770,15 @@ static int flow_launch_locked(IkfFlow* flow, const float* in, int in_ld, const f
       cudaGetLastError();
       flow->cluster_ok = false;
       last_error_ref() = std::string("cluster launch refused (") + cudaGetErrorString(e) + "), clusters disabled for this handle";
-      p.cluster = 1;
-      if (ks) {  // no clusters, no k-split pairs: start over with the plain kernels
-        flow->kern[4] = IkfFlow::Kernel();
-        if (gather) {
-          flow->peer_count_total -= (uint32_t)p.slots * 2u;
-          --flow->peer_seq;
-        }
-        flow->epoch = p.epoch;
-        return flow_launch_locked(flow, in, in_ld, cond, cond_ld, cond_rows, cond_cols, out, out_ld, out_cols, batch, block_first,
-                                  block_last, finalize, clamp, stream, name, forward, logdet_out, gather);
-      }
-      if (gather) flow->peer_count_total -= (uint32_t)p.slots;
-      p.slots = std::min(p.n_rowgroups, flow->slots_max);
+      // start over without clusters (no k-split pairs either): the selection above sees cluster_ok == false
+      if (ks) flow->kern[4] = IkfFlow::Kernel();
       if (gather) {
-        flow->peer_count_total += (uint32_t)p.slots;
-        p.peer_count_target = flow->peer_count_total;
+        flow->peer_count_total -= (uint32_t)p.slots * (ks ? 2u : 1u);
+        --flow->peer_seq;
       }
-      flow->last_cluster = 1;
-      flow->last_grid = p.slots * flow->NT;
-      e = cudaLaunchCooperativeKernel(fn, dim3(p.slots * flow->NT), dim3(threads), args, smem, st);
+      flow->epoch = p.epoch;
+      return flow_launch_locked(flow, in, in_ld, cond, cond_ld, cond_rows, cond_cols, out, out_ld, out_cols, batch, block_first,
+                                block_last, finalize, clamp, stream, name, forward, logdet_out, gather);
     }
   } else {
     e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, st);
