@@ -5,11 +5,20 @@
 //     K-major rows) x RT batch rows (UMMA N = RT, the ACTIVATIONS are the B operand, also K-major), D[128][RT] fp32 in
 //     TMEM: lane = feature, column = row;
 //   * team = hidden/128 CTAs (8 for the released models), one CTA per SM;
-//   * per 64-wide k-chunk: 4 k16 steps x 3 products (tail*head, head*tail, head*head) = 12 tcgen05.mma issued by one
-//     thread, operands straight from the swizzled ring stages (K-major SWIZZLE_128B descriptors), stage release and
-//     "accumulator ready" signalled by tcgen05.commit on mbarriers;
+//   * per 64-wide k-chunk: 4 k16 steps x 3 products (head*head, head*tail, tail*head), folded into 8 tcgen05.mma by
+//     stacking the activation head and tail along N; issued by one elected thread, operands straight from the swizzled
+//     ring stages (K-major SWIZZLE_128B descriptors), stage release and "accumulator ready" signalled by tcgen05.commit
+//     on mbarriers;
 //   * epilogue warps: tcgen05.ld (thread = feature), bias + LeakyReLU, head/tail split, publish; first and last layer
 //     of every subnet in fp32 FMA as before.
+// One kernel template, flow_inverse_umma_kernel<RT, JIT, F16, KS, PP>:
+//   RT   rows of a row group (of a CTA's share of it): 32 / 64 / 128
+//   JIT  just-in-time first layer (RT = 32)                                   -- Cfg, "JIT" below
+//   F16  fp16x3 operand format (scaled fp16 tails, correction products in their own accumulator) instead of bf16x3
+//   KS   k-split pairs: two CTAs (a cluster) share a 64-row group, each multiplies half of the k-chunks; the kernel of
+//        batches up to 576 rows                                                -- Cfg, "KS"
+//   PP   ping-pong: two independent row groups per CTA, the SIMT phases of one under the MMAs of the other; the kernel
+//        of every larger batch (2 x 32 / 64 / 128 rows)                        -- Cfg, "PP"
 // Requires hidden % 128 == 0 and hidden <= 1024.
 #pragma once
 
@@ -33,10 +42,6 @@ constexpr int kAStrideU = 2 * 2 * kRTMaxU * kKC * 2;  // scratch bytes reserved 
 // staging -- the producers store from registers and the consumers poll the data itself.
 constexpr int kPartUnits = kPad / 2;            // 16-byte units per row
 constexpr int kPartRowBytes = kPartUnits * 16;  // 128
-// One bulk copy keeps its issuing thread busy for ~0.3-0.45 us whatever its size; copies issued by different warps run
-// concurrently (scripts/ubench/ingest2.cu).  Four loader warps take the k-chunks round robin so that four copies are
-// always being issued.
-constexpr int kLoaderWarps = 4;
 // per (subnet, feature tile) small fp32 parameters:
 //   first_wT [16 k][128 f] | first_b [128] | big_b [kMaxBig][128] | last_w [16 o][128 f] (float4 slots swizzled, see
 //   flow.cu) | last_b [16]
@@ -507,7 +512,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
   using C = Cfg<RT, JIT, KS, PP>;
   constexpr int XR = C::kXRows;  // rows of a row group (of the exchanged tiles, of the MMAs); RT = rows this CTA finishes
   constexpr int kStages = C::kStages;
-  constexpr int G = C::kGroups, ER = C::kEpiRows, ET = C::kEpiThreads;
+  constexpr int ER = C::kEpiRows, ET = C::kEpiThreads;
   // Accumulator tiles per hidden layer: k-chunk i goes to tile i % kAcc, the epilogue adds the tiles in a fixed order.
   // The tensor core TRUNCATES its fp32 accumulator after every k16 step (a CPU emulation with round-toward-zero reproduces
   // the measured errors, scripts/precision_study.py), a bias that grows with the number of sequential steps: 64 per layer
