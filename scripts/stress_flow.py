@@ -22,4 +22,4 @@ for i in range(iters):
     if not torch.equal(out, ref):
         bad += 1; worst = max(worst, (out - ref).abs().max().item())
 torch.cuda.synchronize()
-print(f"SYNC={os.environ.get('IKFLOW_B200_SYNC','0')} batch {batch}: {bad}/{iters} calls differ from the first (worst {worst:.3e}); status {solver.nn_model.status()}")
+print(f"batch {batch} {solver.nn_model.last_kernel().split('kernel')[-1]}: {bad}/{iters} calls differ from the first (worst {worst:.3e}); status {solver.nn_model.status()}")
