@@ -401,6 +401,22 @@ def extra_block(args, rank, world, dev, flush, headline_solver):
 
     # ---- single-GPU only from here -------------------------------------------------------------------------------------
     solver = headline_solver
+    # large-batch throughput of the headline model, default precision and bf16x3
+    lb = {}
+    for prec in (None, "bf16x3"):
+        s2 = solver
+        if prec is not None:
+            os.environ["IKFLOW_B200_PRECISION"] = prec
+            s2, _ = ikflow_b200.get_ik_solver(HEADLINE_MODEL, synthetic_seed=0)
+            os.environ.pop("IKFLOW_B200_PRECISION", None)
+        for b in (2048, 8192, 9216):
+            q, poses = s2.robot.sample_joint_angles_and_poses(b, seed=80, return_torch=True, device=dev)
+            latent = torch.randn(b, 7, generator=torch.Generator().manual_seed(8)).to(dev)
+            p50, mean = time_calls(lambda: s2.generate_ik_solutions(poses, latent=latent), 20, 5, flush)
+            lb[f"b{b}_{s2.nn_model.effective_precision()}"] = {"p50_ms": p50, "value": b / (mean * 1e-3), "unit": UNIT, "kernel": s2.nn_model.last_kernel()}
+        if prec is not None:
+            del s2
+    extra["large_batch_" + HEADLINE_MODEL.split("__")[0]] = lb
     # latency floor
     for b in (16, 64):
         q, poses = solver.robot.sample_joint_angles_and_poses(b, seed=79, return_torch=True, device=dev)
