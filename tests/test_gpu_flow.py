@@ -62,7 +62,7 @@ def test_golden_fixtures(name):
     assert solver.nn_model.status() == 0
 
 
-@pytest.mark.parametrize("batch", [1, 5, 31, 32, 33, 64, 65, 200, 512, 577, 1000, 1153, 2048])
+@pytest.mark.parametrize("batch", [1, 5, 31, 32, 33, 64, 65, 200, 512, 576, 577, 1000, 1152, 1153, 2048, 2304])
 def test_panda_full_model_parity_all_batch_shapes(batch):
     solver, hp, sd = _solver(12, 7, 3, 1024)
     latent, poses, cond = _inputs(batch, 7)
