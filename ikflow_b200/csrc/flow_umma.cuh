@@ -147,7 +147,7 @@ struct Cfg {
   // which is idle while it is needed (nothing is exchanged between the end of a subnet's second hidden layer and the
   // publication of the next subnet's first layer).
   static constexpr bool kSplit = !JIT;
-  static constexpr int kWStages = PP ? (RT == 128 ? 2 : 3) : ((RT == 128 || KS) ? 3 : 4);
+  static constexpr int kWStages = PP ? (RT == 128 ? 2 : (RT == 64 ? 3 : 4)) : ((RT == 128 || KS) ? 3 : 4);
   static constexpr int kAStages = RT == 128 ? 2 : ((RT == 64 || KS) ? 3 : 4);
   static constexpr int kRecvBytes = KS ? 2 * RT * kFTU * 4 : 16;  // k-split: the peer's partial sums of this CTA's rows, 2 x [32][128] fp32
   // loader warp w owns the ring stages s with s % kLoaders == w: its waits on a stage's barriers are then strictly in
