@@ -143,6 +143,7 @@ struct IkfFlow {
   // k-split pairs for batches of up to ks_slots_max x 64 rows (IKFLOW_B200_KSPLIT=0|1 overrides the default)
   bool ksplit = kDefaultKSplit;
   int ks_slots_max = 0;
+  int ks_private = 2;  // FlowParams::ks_private for hidden = 1024 (IKFLOW_B200_KS_PRIVATE=0|2|4|8)
   // ping-pong kernel for batches of more than one wave of 128-row groups (IKFLOW_B200_PP=0|1)
   bool pingpong = true;
   bool cluster_ok = true;  // cleared if the driver refuses a cooperative launch with clusters
@@ -474,6 +475,10 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   }
   if (!f->jit) f->kern[3] = IkfFlow::Kernel();
   if (const char* env = std::getenv("IKFLOW_B200_KSPLIT")) f->ksplit = std::atoi(env) != 0;
+  if (const char* env = std::getenv("IKFLOW_B200_KS_PRIVATE")) {
+    const int v = std::atoi(env);
+    if (v >= 0 && v <= 8 && v % 2 == 0) f->ks_private = v;
+  }
   if (!f->ksplit || KCH % 4 != 0 || NT > 16) f->kern[4] = IkfFlow::Kernel();  // (flag bits: 2 NT <= 32; whole chunk pairs per half)
   if (const char* env = std::getenv("IKFLOW_B200_PP")) f->pingpong = std::atoi(env) != 0;
   if (!f->pingpong || f->kern[5].smem > (size_t)prop.sharedMemPerBlockOptin) f->kern[5] = IkfFlow::Kernel();
@@ -709,6 +714,7 @@ static int flow_launch_locked(IkfFlow* flow, const float* in, int in_ld, const f
   }
   p.cluster = cs;
   p.ksplit = ks ? 1 : 0;
+  p.ks_private = (ks && flow->base.H / 64 == 16) ? flow->ks_private : 0;  // (hidden = 1024: 12 split + 4 private chunks)
   p.n_peers = 0;
   if (gather) {
     p.n_peers = flow->n_ranks;

@@ -80,6 +80,9 @@ struct FlowParams {
   // k-split pairs (flow_umma.cuh, Cfg::KS): cluster = 2, r = the CTA's half kh of the k-chunks and of the rows,
   // slot = c / NT
   int ksplit;
+  // k-split: the LAST ks_private k-chunks of every hidden layer are multiplied by BOTH CTAs of a pair, each for its own
+  // rows only, so that the hand-over of the split part hides behind them (0: plain split in two halves)
+  int ks_private;
   // Fused gather of the batch-sharded solve (tcgen05 engine; n_peers = 0: off).  The ranks of one node each solve a
   // contiguous block of rows; instead of a collective after the kernel, the final epilogue stores its rows straight into
   // the gathered buffer of EVERY rank (peer-mapped pointers: NVLink stores), and the last CTA to finish raises this

@@ -209,7 +209,7 @@ struct __align__(1024) Smem {
   uint64_t dfull[2], dempty[2];  // per group (ping-pong: two)
   int vt_lock;
   uint64_t rbar;   // k-split: "the peer's partial sums have arrived" (one phase per hidden layer, 32 KB of st.async bytes)
-  uint64_t dhalf;  // k-split: the accumulator tile of the first half of the chunks is complete
+  uint64_t dpart[2];  // k-split: the accumulator tile of the first / second part of the split chunks is complete
   uint32_t tmem_base;
 };
 
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
   // while the second is still being multiplied); 8 chunks per layer and CTA -> the same 16 steps per tile as above
   constexpr int kAcc = KS ? 2 : (PP ? (F16 ? (XR == 128 ? 1 : (XR == 64 ? 2 : 4)) : 1) : (F16 ? (XR == 128 ? 2 : 4) : 1));  // ping-pong: the other half of TMEM belongs to the other group
   constexpr int NG = PP ? 2 : 1;  // independent row groups per CTA
-  constexpr int kTmemColsK = PP ? (2 * kAcc * C::kAccCols <= 128 ? 128 : (2 * kAcc * C::kAccCols <= 256 ? 256 : 512)) : kAcc * C::kAccCols <= 32 ? 32 : (kAcc * C::kAccCols <= 64 ? 64 : (kAcc * C::kAccCols <= 128 ? 128 : (kAcc * C::kAccCols <= 256 ? 256 : 512)));
+  constexpr int kTmemColsK = KS ? 512 : PP ? (2 * kAcc * C::kAccCols <= 128 ? 128 : (2 * kAcc * C::kAccCols <= 256 ? 256 : 512)) : kAcc * C::kAccCols <= 32 ? 32 : (kAcc * C::kAccCols <= 64 ? 64 : (kAcc * C::kAccCols <= 128 ? 128 : (kAcc * C::kAccCols <= 256 ? 256 : 512)));
   static_assert(NG * kAcc * C::kAccCols <= 512 && C::kMmaWarps == 1, "TMEM has 512 columns; the tiles are dealt by chunk index");
   extern __shared__ uint8_t smem_raw[];
   Smem<RT, JIT, KS, PP>& sm = *reinterpret_cast<Smem<RT, JIT, KS, PP>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -535,7 +535,15 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
   const int KCH = p.H / kKC;      // 64-wide k-chunks per hidden layer (2 per producer)
   int slot, t, kh;                // k-split: kh = this CTA's half of the k-chunks = its half of the row group's rows
   cta_coords(p, slot, t, kh);
-  const int KCHL = KS ? KCH / 2 : KCH;  // k-chunks this CTA multiplies per hidden layer
+  // k-split with private chunks (FlowParams::ks_private = KP > 0): chunks [0, KCH - KP) are split between the two CTAs of
+  // the pair (KSH each, multiplied against all 64 rows, partial sums of the peer's rows handed over), chunks [KCH - KP,
+  // KCH) are multiplied by BOTH CTAs against their own 32 rows only -- while the hand-over is on its way
+  const int KP = KS ? p.ks_private : 0;
+  const int KSH = KS ? (KCH - KP) / 2 : 1;  // (1 without k-split: only ever a divisor there)
+  const int KCHL = KS ? KSH + KP : KCH;  // k-chunks this CTA multiplies per hidden layer
+  // i-th chunk of this CTA's layer job -> k-chunk index (fixed consumption order, rotated by the tile index so that the
+  // CTAs of a team do not all pull the same producer's chunk first); i >= KSH: a private chunk
+  auto ks_chunk = [&](int i) { return i < KSH ? KSH * kh + (2 * t + i) % KSH : 2 * KSH + (2 * t + (i - KSH)) % (KP > 0 ? KP : 1); };
   const int xrow0 = KS ? RT * kh : 0;   // this CTA's rows inside the row group / the exchanged tiles
   const int FW = KS ? 2 : 1;            // publication flags per feature tile
   // CTAs per cluster: same t, neighbouring teams (FlowParams::cluster).  Read from the parameter bank where needed
@@ -569,7 +577,8 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
     sm.vt_lock = 0;
     mbar_init(&sm.rbar, 1);
     if (KS) mbar_arrive_expect_tx(&sm.rbar, C::kRecvBytes);  // first phase: two hand-overs of [32 rows][128 features] fp32
-    mbar_init(&sm.dhalf, 1);
+    mbar_init(&sm.dpart[0], 1);
+    mbar_init(&sm.dpart[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
@@ -696,7 +705,8 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
       const uint8_t* wnext =
           reinterpret_cast<const uint8_t*>(p.big_w) + (((size_t)n2 * p.n_big + l2) * NT + t) * KCH * kWChunkU;
       for (int k = lane; k < KCH; k += 32)
-        if (k % p.slots == slot && (!KS || k / KCHL == kh)) bulk_prefetch_l2(wnext + (size_t)k * kWChunkU, kWChunkU);  // (k-split: own half only)
+        if (k % p.slots == slot && (!KS || (k < 2 * KSH ? k / KSH == kh : (k & 1) == kh)))  // (k-split: own half of the split part, every other private chunk)
+          bulk_prefetch_l2(wnext + (size_t)k * kWChunkU, kWChunkU);
     };
     if constexpr (!JIT) {
       // ===== split rings (see Cfg::kSplit): loader warp 0 streams the weights, loader warp 1 the exchanged activations;
@@ -715,7 +725,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
               const uint32_t use = pos / C::kWStages;
               // fixed consumption order (the accumulation order never depends on timing), starting at the CTA's own chunks;
               // k-split: inside this CTA's half of the layer
-              const int kc = KS ? KCHL * kh + (2 * t + i) % KCHL : (2 * t + i) % KCH;
+              const int kc = KS ? ks_chunk(i) : (2 * t + i) % KCH;
               if (use > 0) mbar_wait_relaxed(&sm.wempty[st], (use - 1) & 1);  // clusters: free in EVERY CTA of the cluster
               if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 32 + i);
               if (lane == st) {
@@ -757,9 +767,11 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
             for (int i = 0; i < KCHL; ++i, ++pos) {
               const int st = pos % C::kAStages;
               const uint32_t use = pos / C::kAStages;
-              const int kc = KS ? KCHL * kh + (2 * t + i) % KCHL : (2 * t + i) % KCH;
+              const int kc = KS ? ks_chunk(i) : (2 * t + i) % KCH;
               const int c = kc >> 1;
-              const uint32_t need = KS ? (3u << (2 * c)) : (1u << c);  // k-split: both halves of the producer tile's rows
+              const bool priv = KS && i >= KSH;  // a private chunk: this CTA's own 32 rows only
+              // k-split: both halves of the producer tile's rows (a private chunk: the half that holds this CTA's rows)
+              const uint32_t need = KS ? (priv ? (1u << (2 * c + kh)) : (3u << (2 * c))) : (1u << c);
               if (use > 0) mbar_wait_relaxed(&sm.aempty[st], (use - 1) & 1);
               if (p.trace != nullptr && lane == 0 && i < 16) trace_clk(p, g * 4 + l, 64 + i);
               uint32_t spins = 0;
@@ -790,8 +802,16 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
                 }
               }
               if (lane == st) {
-                mbar_arrive_expect_tx(&sm.afull[st], C::kAChunk);
-                bulk_g2s(sm.aring[st], abase + (size_t)c * kAStrideU + (size_t)(kc & 1) * C::kAChunk, C::kAChunk, &sm.afull[st]);
+                const uint8_t* src = abase + (size_t)c * kAStrideU + (size_t)(kc & 1) * C::kAChunk;
+                if (priv) {
+                  // the own rows of the head and of the tail plane, stacked in the stage as [head 32 rows | tail 32 rows]
+                  mbar_arrive_expect_tx(&sm.afull[st], C::kAChunk / 2);
+                  bulk_g2s(sm.aring[st], src + (size_t)xrow0 * (kKC * 2), C::kAPlane / 2, &sm.afull[st]);
+                  bulk_g2s(sm.aring[st] + C::kAPlane / 2, src + C::kAPlane + (size_t)xrow0 * (kKC * 2), C::kAPlane / 2, &sm.afull[st]);
+                } else {
+                  mbar_arrive_expect_tx(&sm.afull[st], C::kAChunk);
+                  bulk_g2s(sm.aring[st], src, C::kAChunk, &sm.afull[st]);
+                }
                 if (i == 0 && hh == 0) trace_ev(p, g * 4 + l, 1);
               }
               __syncwarp();
@@ -974,14 +994,26 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
               const uint64_t dwh = d_w0 + (uint64_t)(sw * (kWChunkU >> 4)), da = d_as0 + (uint64_t)(sa * (C::kAChunk >> 4));
               if (elect_one()) {
                 // accumulator tile of this chunk (k-split: first / second half of the CTA's chunks)
-                const int tile = KS ? (i >= KCHL / 2 ? 1 : 0) : i % kAcc;
-                const bool accum = KS ? (i != 0 && i != KCHL / 2) : i >= kAcc;
+                // k-split: tiles 0 / 1 = first / second half of the CTA's split chunks, handed over one after the other; the private
+                // chunks (N = the CTA's own 32 rows) go to a third tile behind them
+                const bool priv = KS && KP > 0 && i >= KSH;
+                const int KH1 = (KSH + 1) / 2;  // split chunks of the first tile
+                const int tile = KS ? (priv ? 2 : (i >= KH1 ? 1 : 0)) : i % kAcc;
+                const bool accum = KS ? (i != 0 && i != KH1 && i != KSH) : i >= kAcc;
                 const uint32_t tmem_u = tmem_u0 + (uint32_t)(tile * C::kAccCols) + (PP ? (uint32_t)(hh * kAcc * C::kAccCols) : 0u);
-                if (x3)
+                if (priv) {
+                  constexpr uint32_t idesc_p = make_idesc(kFTU, RT, F16), idesc2_p = make_idesc(kFTU, 2 * RT, F16);
+                  if (x3)
+                    mma_chunk_x3(tmem_u, tmem_u + (F16 ? RT : 0), idesc2_p, idesc_p, dwh, dwh + (uint64_t)(kWPlaneU >> 4), da, accum);
+                  else
+                    mma_chunk_x1(tmem_u, idesc_p, dwh, da, accum);
+                } else if (x3)
                   mma_chunk_x3(tmem_u, tmem_u + kCorrOff, idesc2, idesc, dwh, dwh + (uint64_t)(kWPlaneU >> 4), da, accum);
                 else
                   mma_chunk_x1(tmem_u, idesc, dwh, da, accum);
-                if (KS && i == KCHL / 2 - 1) mma_commit(&sm.dhalf);  // the first tile is complete: its hand-over starts now
+                // a tile of the split part is complete: its hand-over starts now
+                if (KS && i == KH1 - 1) mma_commit(&sm.dpart[0]);
+                if (KS && i == KSH - 1) mma_commit(&sm.dpart[1]);
                 // both stages are free once these MMAs have read them (clusters: the weight stage is refilled by every CTA)
                 if (!KS && p.cluster > 1) mma_commit_multicast(&sm.wempty[sw], (uint16_t)((1u << p.cluster) - 1u)); else mma_commit(&sm.wempty[sw]);
                 mma_commit(&sm.aempty[sa]);
@@ -1250,7 +1282,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
                   //      is handed over while the tensor core still works on the second: only the second hand-over is exposed ----
 #pragma unroll
                   for (int m = 0; m < 2; ++m) {
-                    if (m == 0) mbar_wait(&sm.dhalf, layers & 1); else mbar_wait(&sm.dfull[0], layers & 1);
+                    mbar_wait(&sm.dpart[m], layers & 1);  // tile m of the split part is complete
                     tc_fence_after();
                     if (tid == 0 && m == 1) trace_ev(p, g * 4 + l - 1, 7);
                     // the peer's rows first (it waits for them); the loads of the own rows are in flight while those go out
@@ -1286,6 +1318,21 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
                     if (tid == 0 && m == 1) trace_ev(p, g * 4 + l - 1, 13);
 #pragma unroll
                     for (int r = 0; r < 32; ++r) v[r] = m == 0 ? tmp[r] : v[r] + tmp[r];
+                  }
+                  mbar_wait(&sm.dfull[0], layers & 1);
+                  if (KP > 0) {
+                    // the private chunks' tile: this CTA's own rows only (nothing to hand over)
+                    tc_fence_after();
+                    float tmp[32], tmp2[32];
+                    if (x3) {
+                      tmem_ld32x2(taddr + 2 * C::kAccCols, taddr + 2 * C::kAccCols + RT, tmp, tmp2);
+#pragma unroll
+                      for (int r = 0; r < 32; ++r) v[r] += F16 ? fmaf(tmp2[r], 1.f / kTailScaleF16, tmp[r]) : tmp[r] + tmp2[r];
+                    } else {
+                      tmem_ld32(taddr + 2 * C::kAccCols, tmp);
+#pragma unroll
+                      for (int r = 0; r < 32; ++r) v[r] += tmp[r];
+                    }
                   }
                 } else {
 #pragma unroll
@@ -1330,12 +1377,13 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
                   if (tid == 0) mbar_arrive_expect_tx(&sm.rbar, C::kRecvBytes);  // the next layer's phase
                   const uint32_t rv = smem_u32(sm.recv) + (uint32_t)(f * (RT * 4));
 #pragma unroll
-                  for (int m = 0; m < 2; ++m)
+                  for (int m = 0; m < 2; ++m) {
 #pragma unroll
                     for (int j = 0; j < RT / 4; ++j) {
                       const float4 x = lds128(rv + (uint32_t)(m * kFTU * RT * 4 + ((j ^ (f & 7)) << 4)));
                       v[4 * j] += x.x, v[4 * j + 1] += x.y, v[4 * j + 2] += x.z, v[4 * j + 3] += x.w;
                     }
+                  }
                 }
                 const float bb = lds32(sp_a + (kSmBigB - C::kSmShift + (l - 1) * kFTU + f) * 4);
 #pragma unroll
