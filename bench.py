@@ -706,11 +706,7 @@ def main():
                 "issued_flops_per_launch": 3 * fl * B if precision != "bf16x1" else fl * B,
                 "hbm": {"algorithmic_bytes_per_launch": wbytes + B * 84, "achieved_gbs": (wbytes + B * 84) / (kernel_ms * 1e-3) / 1e9,
                         "peak_gbs": peaks["hbm_gbs"], "frac": (wbytes + B * 84) / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
-                "traffic_source": traffic_src if traffic is not None else (
-                    "none: ncu cannot profile a cooperative launch in thread-block clusters (LaunchFailed under kernel and application "
-                    "replay), which is how the k-split kernel of this batch runs; the unclustered just-in-time kernel of the same batch "
-                    "reads 205.6 MB and writes 4.7 MB of DRAM per launch against 203.5 MB of weights (profiles/r2_flow_umma_b512_ncu_summary.txt)"
-                    if "ksplit" in kernel_name else None),
+                "traffic_source": traffic_src if traffic is not None else "none: no committed ncu capture of this kernel variant at this batch size",
             },
             "status_word": status,
         }

@@ -120,6 +120,7 @@ struct IkfFlow {
   // developer switches, read ONCE when the handle is created (IKFLOW_B200_RT / _DEBUG)
   int forced_rt = 0;
   int debug = 0;
+  bool profiling_launch = false;  // IKFLOW_B200_PROFILING_LAUNCH: see flow_launch_locked
   // Mirror of the device status word in mapped host memory, written by the kernel itself when it gives up on a wait:
   // [0] status bits, [1] id of the aborted launch.  Read without any synchronisation by the next call on the handle.
   volatile uint32_t* status_host = nullptr;
@@ -232,6 +233,7 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
     if (v == 32 || v == 64 || (v == 128 && engine)) f->forced_rt = v;
   }
   if (const char* env = std::getenv("IKFLOW_B200_DEBUG")) f->debug = std::atoi(env);
+  if (const char* env = std::getenv("IKFLOW_B200_PROFILING_LAUNCH")) f->profiling_launch = std::atoi(env) != 0;
   const int FT = engine ? umma::kFTU : kFT;  // hidden features per CTA
   const int NT = H / FT;                     // CTAs per team
   const int KCH = H / kKC;                   // 64-wide k-chunks per hidden layer
@@ -770,6 +772,13 @@ static int flow_launch_locked(IkfFlow* flow, const float* in, int in_ld, const f
     attrs[1].val.clusterDim.x = cs, attrs[1].val.clusterDim.y = 1, attrs[1].val.clusterDim.z = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = 2;
+    if (flow->profiling_launch) {
+      // IKFLOW_B200_PROFILING_LAUNCH=1 (ncu only): the cluster launch WITHOUT the cooperative attribute.  ncu cannot launch
+      // cooperative grids in clusters; under the profiler kernels run alone, and a grid of at most one CTA per SM is then
+      // co-resident anyway.  Never for production: nothing guarantees co-residency here.
+      cfg.attrs = attrs + 1;
+      cfg.numAttrs = 1;
+    }
     e = cudaLaunchKernelExC(&cfg, fn, args);
     if (e != cudaSuccess) {
       // the driver will not place this grid in clusters: remember it and fall back to the plain launch (nothing ran)
