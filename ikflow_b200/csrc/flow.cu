@@ -125,8 +125,10 @@ struct IkfFlow {
   // [0] status bits, [1] id of the aborted launch.  Read without any synchronisation by the next call on the handle.
   volatile uint32_t* status_host = nullptr;
   const char* last_kernel = "";
-  // the kernels of this handle (engine, operand format): [0] 32-row groups, [1] 64, [2] 128 (tcgen05 only), [3] 32 with
-  // the just-in-time first layer (tcgen05 only)
+  // the kernels of this handle (engine, operand format): single row group per CTA: [0] 32 rows, [1] 64, [2] 128 (tcgen05
+  // only), [3] 32 with the just-in-time first layer (tcgen05 only); what a launch picks (flow_launch_locked): [4] k-split pairs
+  // up to 576 rows, [7] / [6] / [5] ping-pong with two 32- / 64- / 128-row groups per CTA beyond; [0]-[3] when those are
+  // switched off, refused by the driver or not applicable (mma.sync engine, IKFLOW_B200_RT)
   struct Kernel {
     const void* fn = nullptr;
     int threads = 0;
