@@ -997,7 +997,8 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
                 // k-split: tiles 0 / 1 = first / second half of the CTA's split chunks, handed over one after the other; the private
                 // chunks (N = the CTA's own 32 rows) go to a third tile behind them
                 const bool priv = KS && KP > 0 && i >= KSH;
-                const int KH1 = (KSH + 1) / 2;  // split chunks of the first tile
+                // split chunks of the first tile (IKFLOW_B200_DEBUG 8192 / 16384: one less / one more, for A/B runs; valid results)
+                const int KH1 = (KSH + 1) / 2 - ((p.debug & 8192) ? 1 : 0) + ((p.debug & 16384) ? 1 : 0);
                 const int tile = KS ? (priv ? 2 : (i >= KH1 ? 1 : 0)) : i % kAcc;
                 const bool accum = KS ? (i != 0 && i != KH1 && i != KSH) : i >= kAcc;
                 const uint32_t tmem_u = tmem_u0 + (uint32_t)(tile * C::kAccCols) + (PP ? (uint32_t)(hh * kAcc * C::kAccCols) : 0u);
