@@ -121,6 +121,8 @@ struct IkfFlow {
   int forced_rt = 0;
   int debug = 0;
   bool profiling_launch = false;  // IKFLOW_B200_PROFILING_LAUNCH: see flow_launch_locked
+  bool tail_split = true;          // IKFLOW_B200_TAIL_SPLIT=0|1: see flow_launch
+  int row_base = 0;                // FlowParams::row_base of the next launch (set under the lock)
   // Mirror of the device status word in mapped host memory, written by the kernel itself when it gives up on a wait:
   // [0] status bits, [1] id of the aborted launch.  Read without any synchronisation by the next call on the handle.
   volatile uint32_t* status_host = nullptr;
@@ -236,6 +238,7 @@ int ikf_flow_create(const IkfFlowDesc* desc, const float* weights, size_t n_weig
   }
   if (const char* env = std::getenv("IKFLOW_B200_DEBUG")) f->debug = std::atoi(env);
   if (const char* env = std::getenv("IKFLOW_B200_PROFILING_LAUNCH")) f->profiling_launch = std::atoi(env) != 0;
+  if (const char* env = std::getenv("IKFLOW_B200_TAIL_SPLIT")) f->tail_split = std::atoi(env) != 0;
   const int FT = engine ? umma::kFTU : kFT;  // hidden features per CTA
   const int NT = H / FT;                     // CTAs per team
   const int KCH = H / kKC;                   // 64-wide k-chunks per hidden layer
@@ -597,6 +600,25 @@ static int flow_launch(IkfFlow* flow, const float* in, int in_ld, const float* c
                        const GatherArgs* gather = nullptr) {
   if (!flow) return fail(IKF_EINVAL, "%s: flow is NULL", name);
   std::lock_guard<std::mutex> lock(flow->mu);  // see IkfFlow::mu
+  // Tail split: the ping-pong kernel with 128-row groups works in rounds of slots_max x 256 rows, and a partly filled last
+  // round costs as much as a full one.  A remainder that a smaller kernel finishes faster (up to one wave of 128-row
+  // groups) goes into a second launch of its own.  (Not with the fused gather: the ranks must agree on the launches.)
+  if (flow->engine && flow->kern[5].fn && flow->tail_split && !flow->forced_rt && gather == nullptr && in && out) {
+    const int round_rows = flow->slots_max * 2 * 128;
+    const int rem = batch % round_rows;
+    if (batch > round_rows && rem > 0 && rem <= flow->slots_max * 128) {
+      const int first = batch - rem;
+      int rc = flow_launch_locked(flow, in, in_ld, cond, cond_ld, cond_rows, cond_cols, out, out_ld, out_cols, first, block_first, block_last,
+                                  finalize, clamp, stream, name, forward, logdet_out, nullptr);
+      if (rc != IKF_OK) return rc;
+      flow->row_base = first;
+      rc = flow_launch_locked(flow, in + (size_t)first * in_ld, in_ld, cond, cond_ld, cond_rows, cond_cols, out + (size_t)first * out_ld, out_ld,
+                              out_cols, rem, block_first, block_last, finalize, clamp, stream, name, forward,
+                              logdet_out ? logdet_out + first : nullptr, nullptr);
+      flow->row_base = 0;
+      return rc;
+    }
+  }
   return flow_launch_locked(flow, in, in_ld, cond, cond_ld, cond_rows, cond_cols, out, out_ld, out_cols, batch, block_first, block_last,
                             finalize, clamp, stream, name, forward, logdet_out, gather);
 }
@@ -636,6 +658,7 @@ static int flow_launch_locked(IkfFlow* flow, const float* in, int in_ld, const f
   p.in = in; p.in_ld = in_ld; p.cond = cond; p.cond_ld = cond_ld; p.cond_rows = cond_rows; p.cond_cols = cond_cols;
   p.out = out; p.out_ld = out_ld; p.out_cols = out_cols; p.batch = batch;
   p.block_first = block_first; p.block_last = block_last; p.finalize = finalize; p.clamp_out = clamp;
+  p.row_base = flow->row_base;
   p.forward = forward; p.logdet_out = logdet_out; p.logdet_m = flow->logdet_m;
   {
     // PermuteRandom folded into the indexing of the flow state (FlowParams::phys)

@@ -73,6 +73,7 @@ struct FlowParams {
   float* out;
   int in_ld, cond_ld, cond_rows, cond_cols, out_ld, out_cols;
   int batch, block_first, block_last, finalize, clamp_out, n_rowgroups, slots;
+  int row_base;  // row 0 of this launch is row `row_base` of the caller's batch (the condition of row i is row (row_base + i) % cond_rows)
   // tcgen05 engine: CTAs per thread-block cluster (1 = no clusters).  A cluster holds the CTAs with the SAME feature tile
   // t of `cluster` neighbouring teams: they need the same weight chunks at the same time, so each loads 1/cluster of a
   // chunk and multicasts it to all of them (one L2 read instead of `cluster`).  CTA -> (team slot, feature tile t):

@@ -1129,7 +1129,7 @@ __global__ void __launch_bounds__(Cfg<RT, JIT, KS, PP>::kThreads, 1) flow_invers
         float uv = 0.f, cv = 0.f;
         if (row < p.batch) {
           if (j < p.W) uv = p.in[(size_t)row * p.in_ld + j];
-          if (j < p.cond_cols) cv = p.cond[(size_t)(row % p.cond_rows) * p.cond_ld + j];
+          if (j < p.cond_cols) cv = p.cond[(size_t)((p.row_base + row) % p.cond_rows) * p.cond_ld + j];
         }
         su[r][j] = uv;
         if (j < 8) scnd[r][j] = cv;

@@ -619,6 +619,7 @@ def test_pingpong_kernel_matches_oracle_and_the_single_group_kernel(batch, preci
     """Two 32- (577 .. 1152 rows), 64- (.. 2304) or 128-row groups per CTA, out of phase.  Same layer arithmetic as the
     single-group kernels, bit for bit -- except fp16x3 at 128 rows, which has one accumulator tile instead of two.  Odd
     numbers of row groups (577 -> 19, 2305 -> 19, 4737 -> 38 = 2 full rounds + 2) walk empty groups."""
+    monkeypatch.setenv("IKFLOW_B200_TAIL_SPLIT", "0")  # (4737 rows would otherwise go as 4608 + 129: test_tail_split_of_large_batches)
     model, hp, sd = _model_with_precision(precision)
     latent, poses, cond = _inputs(batch, 7)
     out = model.inverse(latent.to(DEV), cond.to(DEV))
@@ -656,3 +657,32 @@ def test_pingpong_kernel_forward_pass_and_block_ranges():
     assert "pingpong" in solver.nn_model.last_kernel()
     assert (part.cpu() - inter[1]).abs().max() < TOL
     assert solver.nn_model.status() == 0
+
+
+@pytest.mark.parametrize("batch,cond_rows", [(6144, 2048), (5000, 5000), (4608 + 2304, 1)])
+def test_tail_split_of_large_batches(batch, cond_rows, monkeypatch):
+    """Batches beyond one round of the 128-row ping-pong kernel (4608 rows) whose remainder fits a smaller kernel are solved
+    in two launches (flow.cu, flow_launch): rows [0, k x 4608) by the ping-pong kernel, the rest by the kernel of its own
+    size -- with the condition indexed from the caller's row (repeat-major tiling, one broadcast pose)."""
+    model, hp, sd = _model_with_precision("bf16x3")
+    latent, poses, cond = _inputs(batch, 7)
+    cond_t = cond[:cond_rows]
+    launches0 = ikflow_b200._lib.launch_count()
+    out = model.inverse(latent.to(DEV), cond_t.to(DEV))
+    assert ikflow_b200._lib.launch_count() - launches0 == 2
+    assert ("ksplit" if batch == 5000 else "<64,false,false,pingpong>") in model.last_kernel()  # (the kernel of the remainder)
+    full_cond = cond_t.repeat(batch // cond_rows, 1) if cond_rows < batch else cond_t
+    idx = torch.cat([torch.arange(0, batch, 97), torch.arange(4608 - 3, 4608 + 3), torch.arange(batch - 40, batch)])
+    assert (out.cpu()[idx] - _oracle(sd, hp, latent[idx], full_cond[idx])).abs().max() < TOL
+    monkeypatch.setenv("IKFLOW_B200_TAIL_SPLIT", "0")
+    plain, _, _ = _model_with_precision("bf16x3")
+    launches0 = ikflow_b200._lib.launch_count()
+    ref = plain.inverse(latent.to(DEV), cond_t.to(DEV))
+    assert ikflow_b200._lib.launch_count() - launches0 == 1
+    first = batch - batch % 4608
+    assert torch.equal(ref[:first], out[:first])
+    if batch == 5000:  # remainder of 392 rows: the k-split kernel, same operands in another summation order
+        assert (ref[first:] - out[first:]).abs().max() < 4e-5
+    else:  # the ping-pong kernels of all three sizes and the single-group kernels agree bit for bit in bf16x3
+        assert torch.equal(ref, out)
+    assert model.status() == 0 and plain.status() == 0
