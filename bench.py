@@ -89,11 +89,10 @@ def measured_peaks():
 
 def _kernel_template_args(name: str):
     """('ikf::umma::flow_inverse_umma_kernel<32,false,true,ksplit>' | ncu's '...<128, 0, 1, 0, 1>(...)') -> (engine, [rt, jit, f16, ks, pp])."""
-    tail = name.replace(" ", "").split("flow_inverse")[-1].split("(")[0]
+    tail = name.replace(" ", "").replace("(int)", "").replace("(bool)", "").split("flow_inverse")[-1].split("(")[0]
     engine, _, rest = tail.partition("<")
     vals = []
     for a in rest.rstrip(">").split(","):
-        a = a.replace("(int)", "").replace("(bool)", "")
         if a == "ksplit":
             vals = (vals + [0, 0, 0])[:3] + [1, 0]
         elif a == "pingpong":
